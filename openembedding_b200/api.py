@@ -1,0 +1,638 @@
+"""User-facing API on ``torch.nn`` -- the counterpart of ``openembedding.tensorflow``
+(openembedding/tensorflow/exb.py, 706 lines).
+
+=====================  =================================================================
+reference (exb.py)      here
+=====================  =================================================================
+Variable :222-360       ``Variable`` / ``distributed_variable``
+Embedding :388-443      ``Embedding`` (an ``nn.Module``)
+distributed_optimizer   ``distributed_optimizer`` + ``Adadelta..SGD`` classes (:446-488)
+distributed_model       ``distributed_model`` / ``Model`` (:551-642)
+save/load_server_model  same names (:491-503); ``save_as_original_model`` (:506-547)
+pulling :645-691        ``pulling`` (input-pipeline prefetch)
+persist/restore :697+   same names (host-tier lightweight checkpoint)
+=====================  =================================================================
+
+The reference makes TensorFlow call the PS by attaching a dummy ``[1, dim]`` variable to
+each table and returning a fake gradient for it; the same trick is used here so that any
+``torch.optim`` optimizer wrapped by ``distributed_optimizer`` drives the sparse update
+in ``step()``.
+"""
+import copy
+import math
+import os
+import shutil
+
+import torch
+from torch import nn
+
+from . import checkpoint as _ckpt
+from . import flags  # noqa: F401  (re-export like `from openembedding import *`)
+from .config import HASH_KEY_RANGE, normalize_initializer, normalize_optimizer, str_dict
+from .context import get_context
+
+_HASH_KEY_RANGE = HASH_KEY_RANGE
+
+
+# --------------------------------------------------------------------------- configs
+def _torch_optimizer_config(optimizer, explicit=True):
+    """torch.optim instance -> server optimizer config (keras names; exb.py:66-86)."""
+    if isinstance(optimizer, dict):
+        return normalize_optimizer(optimizer)
+    if not isinstance(optimizer, torch.optim.Optimizer):
+        raise ValueError("error optimizer: " + str(optimizer))
+    g = optimizer.param_groups[0] if optimizer.param_groups else optimizer.defaults
+    name = type(optimizer).__name__.lower()
+    for base in type(optimizer).__mro__:
+        if base.__module__.startswith("torch.optim") and base is not torch.optim.Optimizer:
+            name = base.__name__.lower()
+            break
+    if getattr(optimizer, "_keras_category", None):
+        name = optimizer._keras_category
+    if name in ("adam", "adamw") and g.get("amsgrad", False):
+        if explicit:
+            raise ValueError("not support adam with amsgrad")
+    if name == "rmsprop" and g.get("centered", False):
+        if explicit:
+            raise ValueError("not support centered rmsprop")
+    if float(g.get("lr_decay", 0.0) or 0.0) != 0.0 and explicit:
+        raise ValueError("not support learning rate decay")
+    if float(g.get("weight_decay", 0.0) or 0.0) != 0.0 and explicit:
+        raise ValueError("not support weight_decay on server side embeddings")
+    lr = float(g.get("lr", 0.001))
+    if name == "adagrad":
+        return normalize_optimizer({"category": "adagrad", "learning_rate": lr,
+                                    "initial_accumulator_value": g.get("initial_accumulator_value", 0.0),
+                                    "epsilon": g.get("eps", 1e-10)})
+    if name in ("adam", "adamw"):
+        b1, b2 = g.get("betas", (0.9, 0.999))
+        return normalize_optimizer({"category": "adam", "learning_rate": lr, "beta_1": b1, "beta_2": b2,
+                                    "epsilon": g.get("eps", 1e-8)})
+    if name == "adamax":
+        b1, b2 = g.get("betas", (0.9, 0.999))
+        return normalize_optimizer({"category": "adamax", "learning_rate": lr, "beta_1": b1, "beta_2": b2,
+                                    "epsilon": g.get("eps", 1e-8)})
+    if name == "adadelta":
+        return normalize_optimizer({"category": "adadelta", "learning_rate": lr, "rho": g.get("rho", 0.9),
+                                    "epsilon": g.get("eps", 1e-6)})
+    if name == "rmsprop":
+        return normalize_optimizer({"category": "rmsprop", "learning_rate": lr, "rho": g.get("alpha", 0.99),
+                                    "momentum": g.get("momentum", 0.0), "epsilon": g.get("eps", 1e-8)})
+    if name == "sgd":
+        return normalize_optimizer({"category": "sgd", "learning_rate": lr, "momentum": g.get("momentum", 0.0),
+                                    "nesterov": bool(g.get("nesterov", False))})
+    if name == "ftrl":
+        return normalize_optimizer({"category": "ftrl", "learning_rate": lr,
+                                    "initial_accumulator_value": g.get("initial_accumulator_value", 0.1),
+                                    "l1_regularization_strength": g.get("l1_regularization_strength", 0.0),
+                                    "l2_regularization_strength": g.get("l2_regularization_strength", 0.0),
+                                    "l2_shrinkage_regularization_strength": g.get("l2_shrinkage_regularization_strength", 0.0),
+                                    "learning_rate_power": g.get("learning_rate_power", -0.5),
+                                    "beta": g.get("beta", 0.0)})
+    # Nadam etc.: wrapped by the reference too, but no server implementation exists
+    # (EmbeddingOptimizer.h:393-395) -> fail like its factory does.
+    raise ValueError("unsupported server optimizer: " + name)
+
+
+# --------------------------------------------------------------------------- Variable
+class _SparseRead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph_var, indices, variable):
+        ctx.variable = variable
+        ctx.indices = indices
+        rows = variable._pull(indices)
+        return rows
+
+    @staticmethod
+    def backward(ctx, grad):
+        v = ctx.variable
+        v._push(ctx.indices, grad)
+        return torch.zeros_like(v.graph_var), None, None
+
+
+class Variable:
+    """A server-side (sharded, HBM-resident) embedding variable.
+
+    ``shape[0] == -1`` selects the hashed 2**63 key space (exb.py:231-233).
+    """
+
+    def __init__(self, initializer=None, trainable=None, name=None, dtype=None, shape=None, num_shards=None,
+                 sparse_as_dense=False, graph_var=None):
+        if not num_shards:
+            num_shards = -1
+        if shape is not None:
+            shape = list(shape)
+        if shape is not None and shape[0] == -1:
+            shape[0] = _HASH_KEY_RANGE
+            sparse_as_dense = False
+        if graph_var is not None:
+            if name or trainable is not None:
+                raise ValueError("parameter conflict with graph_var")
+            if shape and list(shape[1:]) != list(graph_var.shape[1:]):
+                raise ValueError("graph_var shape not match")
+        self._initialized = False
+        self._name = name
+        ctx = get_context()
+        if dtype is None:
+            dtype = torch.float32
+        self._tdtype = dtype if isinstance(dtype, torch.dtype) else getattr(torch, str(dtype))
+        if sparse_as_dense:
+            if graph_var is None:
+                init = normalize_initializer(initializer)
+                w = torch.empty(shape, dtype=self._tdtype, device=ctx.device)
+                _dense_init(w, init)
+                graph_var = nn.Parameter(w, requires_grad=trainable is not False)
+            self._sparse_as_dense = True
+            self._shape = list(graph_var.shape)
+            self.graph_var = graph_var
+            return
+        if shape is None or shape[0] <= 0 or shape[0] > _HASH_KEY_RANGE:
+            raise ValueError("error shape")
+        if not isinstance(initializer, dict):
+            initializer = normalize_initializer(initializer)
+        dtype_name = str(self._tdtype).replace("torch.", "")
+        if graph_var is None:
+            graph_var = nn.Parameter(torch.zeros([1] + shape[1:], dtype=self._tdtype, device=ctx.device),
+                                     requires_grad=trainable is not False)
+        embedding_dim = 1
+        for d in shape[1:]:
+            embedding_dim *= d
+        self._sparse_as_dense = False
+        self._shape = shape
+        self._initialized = True
+        self.graph_var = graph_var
+        self.storage = ctx.create_storage(num_shards)
+        self.variable = ctx.create_variable(self.storage, shape[0], embedding_dim, dtype_name)
+        ctx.set_initializer(self.variable, initializer)
+        self.model_uuid = ctx.model_uuid
+        self.optimizer_set = False
+        self._prefetched = []
+        ctx.tracks[id(graph_var)] = self
+
+    # -- properties
+    @property
+    def name(self):
+        return self._name or ("variable_%d" % self.variable.variable_id if not self._sparse_as_dense else "dense")
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def sparse_as_dense(self):
+        return self._sparse_as_dense
+
+    # -- data path
+    def _pull(self, indices):
+        ctx = get_context()
+        flat = indices.reshape(-1)
+        rows = ctx.backend.pull(self.variable, flat)
+        return rows.reshape(tuple(indices.shape) + tuple(self._shape[1:])).to(self._tdtype)
+
+    def _push(self, indices, grads):
+        ctx = get_context()
+        ctx.backend.push(self.variable, indices.reshape(-1), grads.reshape(-1, self.variable.dim))
+
+    def prefetch(self, indices, steps=None):
+        """Stage the ids of a future batch on the device ahead of time.
+
+        The reference parks a future-batch pull on the server until ``batch_id`` catches up
+        (exb_ops.cpp:139-175, EmbeddingPullOperator.cpp:117-145). With tables in HBM the row
+        gather itself is cheap; what is worth overlapping is the host->device copy of ids."""
+        if self.sparse_as_dense:
+            raise ValueError("should not prefetch for sparse as dense.")
+        ctx = get_context()
+        if ctx.device.type == "cuda" and not indices.is_cuda:
+            src = indices if indices.is_pinned() else indices.pin_memory()
+            return src.to(ctx.device, non_blocking=True)
+        return indices
+
+    def sparse_read(self, indices):
+        if self.sparse_as_dense:
+            return nn.functional.embedding(indices.to(self.graph_var.device), self.graph_var)
+        ctx = get_context()
+        if indices.dtype != torch.int64:
+            indices = indices.to(torch.int64)
+        indices = indices.to(ctx.device)
+        if torch.is_grad_enabled() and self.graph_var.requires_grad:
+            return _SparseRead.apply(self.graph_var, indices, self)
+        return self._pull(indices)
+
+    pull_weights = sparse_read
+
+    def set_server_optimizer(self, optimizer):
+        if self.sparse_as_dense:
+            raise ValueError("no need optimizer for sparse as dense.")
+        if not isinstance(optimizer, dict):
+            optimizer = _torch_optimizer_config(optimizer)
+        get_context().set_optimizer(self.variable, optimizer)
+        self.optimizer_set = True
+
+    def push_gradients(self, indices, gradients):
+        if self.sparse_as_dense:
+            raise ValueError("no need update weights for sparse as dense.")
+        self._push(indices.to(torch.int64), gradients)
+        return torch.zeros_like(self.graph_var)
+
+    def update_weights(self, fake_grad=None):
+        if self.sparse_as_dense:
+            raise ValueError("no need update weights for sparse as dense.")
+        get_context().backend.update([self.variable])
+
+    def _finalize(self):
+        self._initialized = False
+
+
+distributed_variable = Variable
+
+
+def _dense_init(w, init):
+    c = init["category"]
+    with torch.no_grad():
+        if c == "constant":
+            w.fill_(init["value"])
+        elif c == "uniform":
+            w.uniform_(init["minval"], init["maxval"])
+        else:
+            w.normal_(init["mean"], init["stddev"])
+
+
+# --------------------------------------------------------------------------- Embedding
+class Embedding(nn.Module):
+    """Drop-in for ``nn.Embedding`` / ``keras.layers.Embedding`` backed by the sharded engine.
+
+    input_dim: vocabulary size; ``-1``/``None`` -> ids in [0, 2**63) (hash table).
+    sparse_as_dense: keep the table as an ordinary replicated parameter with dense
+    gradients (the "cache" mode of the reference, exb.py:241-248).
+    """
+
+    def __init__(self, input_dim, output_dim, embeddings_initializer="uniform", embeddings_regularizer=None,
+                 activity_regularizer=None, embeddings_constraint=None, mask_zero=False, input_length=None,
+                 num_shards=None, sparse_as_dense=False, explicit=True, dtype=None, name=None):
+        super().__init__()
+        if input_dim is None:
+            input_dim = -1
+        if input_dim == -1:
+            input_dim = _HASH_KEY_RANGE
+            sparse_as_dense = False
+        if not sparse_as_dense and explicit:
+            if embeddings_regularizer:
+                raise ValueError("not support embeddings_regularizer")
+            if embeddings_constraint:
+                raise ValueError("not support embeddings_constraint")
+        if not activity_regularizer:
+            activity_regularizer = embeddings_regularizer
+        if input_dim <= 0:
+            raise ValueError("error input_dim")
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.num_shards = num_shards
+        self.sparse_as_dense = bool(sparse_as_dense)
+        self.activity_regularizer = activity_regularizer
+        self.mask_zero, self.input_length = mask_zero, input_length
+        self.layer_name = name
+        self.embeddings_initializer = embeddings_initializer
+        self.server_initializer = normalize_initializer(embeddings_initializer, explicit=explicit)
+        ctx = get_context()
+        dtype = dtype or torch.float32
+        if self.sparse_as_dense:
+            w = torch.empty((self.input_dim, self.output_dim), dtype=dtype, device=ctx.device)
+            _dense_init(w, self.server_initializer)
+            self.embeddings = nn.Parameter(w)
+            self.variable = Variable(sparse_as_dense=True, graph_var=self.embeddings)
+        else:
+            self.embeddings = nn.Parameter(torch.zeros((1, self.output_dim), dtype=dtype, device=ctx.device))
+            self.variable = Variable(initializer=dict(self.server_initializer), dtype=dtype,
+                                     shape=(self.input_dim, self.output_dim), num_shards=num_shards,
+                                     graph_var=self.embeddings)
+        self.built = True
+
+    def forward(self, inputs):
+        out = self.variable.sparse_read(inputs)
+        if self.activity_regularizer is not None and self.training:
+            self.activity_loss = self.activity_regularizer(out)
+        return out
+
+    def extra_repr(self):
+        v = "2**63" if self.input_dim >= _HASH_KEY_RANGE else str(self.input_dim)
+        return "%s, %d, sparse_as_dense=%s" % (v, self.output_dim, self.sparse_as_dense)
+
+
+# --------------------------------------------------------------------------- optimizers
+class Ftrl(torch.optim.Optimizer):
+    """Dense-parameter FTRL with tf.keras semantics (the formulas of
+    openembedding/variable/EmbeddingOptimizer.h:230-293, shared with the server kernels)."""
+    _keras_category = "ftrl"
+
+    def __init__(self, params, lr=0.001, initial_accumulator_value=0.1, l1_regularization_strength=0.0,
+                 l2_regularization_strength=0.0, l2_shrinkage_regularization_strength=0.0,
+                 learning_rate_power=-0.5, beta=0.0):
+        defaults = dict(lr=lr, initial_accumulator_value=initial_accumulator_value,
+                        l1_regularization_strength=l1_regularization_strength,
+                        l2_regularization_strength=l2_regularization_strength,
+                        l2_shrinkage_regularization_strength=l2_shrinkage_regularization_strength,
+                        learning_rate_power=learning_rate_power, beta=beta)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for g in self.param_groups:
+            lr, l1, l2 = g["lr"], g["l1_regularization_strength"], g["l2_regularization_strength"]
+            l2s, p, beta = g["l2_shrinkage_regularization_strength"], -g["learning_rate_power"], g["beta"]
+            adj_l2 = l2 + beta / lr / 2
+            for w in g["params"]:
+                if w.grad is None:
+                    continue
+                st = self.state[w]
+                if not st:
+                    st["accum"] = torch.full_like(w, g["initial_accumulator_value"])
+                    st["linear"] = torch.zeros_like(w)
+                grad = w.grad
+                gg = grad + 2 * l2s * w
+                accum_new = st["accum"] + grad * grad
+                sigma = (accum_new.pow(p) - st["accum"].pow(p)) / lr
+                st["linear"] += gg - sigma * w
+                st["accum"] = accum_new
+                quadratic = accum_new.pow(p) / lr + 2 * adj_l2
+                l1_adj = st["linear"].clamp(-l1, l1)
+                w.copy_((l1_adj - st["linear"]) / quadratic)
+        return loss
+
+
+_DistributedOptimizerClass = {}
+
+
+def _DistributedOptimizer(T):
+    """Subclass of optimizer class T whose ``step`` also drives the server-side update
+    (reference: exb.py:446-468 overriding ``_resource_apply_dense``)."""
+    if T in _DistributedOptimizerClass:
+        return _DistributedOptimizerClass[T]
+
+    class _Optimizer(T):
+        def __init__(self, *args, explicit=True, **kwargs):
+            super().__init__(*args, **kwargs)
+            self._explicit = explicit
+            self.server_optimizer = _torch_optimizer_config(self, explicit=explicit)
+
+        @torch.no_grad()
+        def step(self, closure=None):
+            ctx = get_context()
+            tracked, stash = [], []
+            for g in self.param_groups:
+                for p in g["params"]:
+                    v = ctx.tracks.get(id(p))
+                    if v is not None and not v.sparse_as_dense:
+                        if not v.optimizer_set:
+                            v.set_server_optimizer(self.server_optimizer)
+                        if p.grad is not None:
+                            tracked.append(v)
+                        stash.append((p, p.grad))
+                        p.grad = None          # the dummy [1, dim] parameter is never updated locally
+            if tracked:
+                ctx.backend.update([v.variable for v in tracked])
+            ctx.model_version += 1
+            try:
+                return super().step(closure)
+            finally:
+                for p, gr in stash:
+                    p.grad = gr
+
+    _Optimizer.__name__ = T.__name__
+    _Optimizer.__qualname__ = T.__qualname__
+    _DistributedOptimizerClass[T] = _Optimizer
+    return _Optimizer
+
+
+Adadelta = _DistributedOptimizer(torch.optim.Adadelta)
+Adagrad = _DistributedOptimizer(torch.optim.Adagrad)
+Adam = _DistributedOptimizer(torch.optim.Adam)
+Adamax = _DistributedOptimizer(torch.optim.Adamax)
+Nadam = _DistributedOptimizer(torch.optim.NAdam)   # constructing it raises: no server implementation
+RMSprop = _DistributedOptimizer(torch.optim.RMSprop)
+SGD = _DistributedOptimizer(torch.optim.SGD)
+FtrlDistributed = _DistributedOptimizer(Ftrl)
+
+
+def distributed_optimizer(optimizer, explicit=True):
+    """Return a distributed optimizer that trains dense parameters locally and the
+    server-side embeddings through the sparse engine. If a data-parallel wrapper is
+    used (DDP / ``parallel.allreduce``), create it after this call (exb.py:481-488)."""
+    cls = _DistributedOptimizer(type(optimizer))
+    new = cls.__new__(cls)
+    new.__dict__.update(optimizer.__dict__)
+    new._explicit = explicit
+    new.server_optimizer = _torch_optimizer_config(optimizer, explicit=explicit)
+    return new
+
+
+# --------------------------------------------------------------------------- model save / load
+def save_server_model(model, filepath, include_optimizer=True):
+    """Save the parameters held by the sparse engine. Collective: every rank writes its
+    own shard (there are no server processes to do it on a single caller's behalf)."""
+    ctx = get_context()
+    _ckpt.save_model(ctx, filepath, include_optimizer=include_optimizer)
+
+
+def load_server_model(model, filepath):
+    """Load the server parameters. Must be called synchronously by all workers."""
+    _ckpt.load_model(get_context(), filepath)
+
+
+def _iter_embeddings(model):
+    for name, mod in model.named_modules():
+        if isinstance(mod, Embedding):
+            yield name, mod
+
+
+def _to_original(model):
+    """Deep copy of `model` where every server Embedding became a plain nn.Embedding."""
+    for _, layer in _iter_embeddings(model):
+        if layer.variable.shape[0] >= _HASH_KEY_RANGE:
+            raise ValueError("can not convert sparse variable to nn.Embedding.")
+    ctx = get_context()
+    memo = {}
+    for _, layer in _iter_embeddings(model):   # do not deep-copy engine handles
+        memo[id(layer)] = layer
+    clone = copy.deepcopy(model, memo)
+
+    def convert(parent):
+        for cname, child in list(parent.named_children()):
+            if isinstance(child, Embedding):
+                plain = nn.Embedding(child.input_dim, child.output_dim)
+                if child.sparse_as_dense:
+                    plain.weight.data.copy_(child.embeddings.data)
+                else:
+                    batch = 2 ** 20 // child.output_dim + 1      # exb.py:541
+                    with torch.no_grad():
+                        for i in range(0, child.input_dim, batch):
+                            idx = torch.arange(i, min(child.input_dim, i + batch), device=ctx.device)
+                            plain.weight.data[i:i + idx.numel()] = child.variable.sparse_read(idx).to("cpu")
+                setattr(parent, cname, plain)
+            else:
+                convert(child)
+
+    convert(clone)
+    if isinstance(clone, Embedding):
+        raise ValueError("wrap the Embedding in a module to export it")
+    return clone
+
+
+def save_as_original_model(model, filepath, overwrite=True, include_optimizer=False, **kwargs):
+    """Export a stand-alone PyTorch model (plain ``nn.Embedding`` weights) that needs no
+    engine to serve -- counterpart of exb.py:506-547."""
+    if include_optimizer is True:
+        raise ValueError("not support include optimizer")
+    if os.path.exists(filepath) and not overwrite:
+        raise IOError("exists: " + filepath)
+    clone = _to_original(model)
+    if type(clone).__name__ in _DistributedModelNames:
+        clone.__class__ = clone._Class_base
+    d = os.path.dirname(os.path.abspath(filepath))
+    os.makedirs(d, exist_ok=True)
+    torch.save(clone.cpu(), filepath)
+    return clone
+
+
+_DistributedModelClass = {}
+_DistributedModelNames = set()
+
+
+def _DistributedModel(T):
+    if T in _DistributedModelClass:
+        return _DistributedModelClass[T]
+
+    class _Model(T):
+        _Class_base = T
+
+        def save(self, filepath, overwrite=True, include_optimizer=True, **kwargs):
+            """dense state_dict -> <filepath>/model.pt ; server tables -> <filepath>/openembedding/"""
+            ctx = get_context()
+            if ctx.rank == 0:
+                os.makedirs(filepath, exist_ok=True)
+                torch.save(self.state_dict(), os.path.join(filepath, "model.pt"))
+                if os.path.exists(filepath + "/openembedding"):
+                    shutil.rmtree(filepath + "/openembedding")
+            ctx.barrier()
+            save_server_model(self, filepath + "/openembedding", include_optimizer=include_optimizer)
+
+        def save_weights(self, filepath, **kwargs):
+            ctx = get_context()
+            if ctx.rank == 0:
+                d = os.path.dirname(os.path.abspath(filepath))
+                os.makedirs(d, exist_ok=True)
+                torch.save(self.state_dict(), filepath)
+                if os.path.exists(filepath + ".openembedding/openembedding"):
+                    shutil.rmtree(filepath + ".openembedding/openembedding")
+            ctx.barrier()
+            save_server_model(self, filepath + ".openembedding/openembedding", include_optimizer=True)
+
+        def load_weights(self, filepath, **kwargs):
+            if os.path.isdir(filepath) and os.path.exists(os.path.join(filepath, "model.pt")):
+                self.load_state_dict(torch.load(os.path.join(filepath, "model.pt"), map_location="cpu"))
+                load_server_model(self, filepath + "/openembedding")
+                return
+            self.load_state_dict(torch.load(filepath, map_location="cpu"))
+            if os.path.exists(filepath + ".openembedding/openembedding"):
+                load_server_model(self, filepath + ".openembedding/openembedding")
+            elif os.path.exists(os.path.split(filepath)[0] + "/../openembedding"):
+                load_server_model(self, os.path.split(filepath)[0] + "/../openembedding")
+            else:
+                raise IOError("embed not exist: " + filepath)
+
+        def save_as_original_model(self, filepath, *args, **kwargs):
+            return save_as_original_model(self, filepath, *args, **kwargs)
+
+    _Model.__name__ = T.__name__
+    _Model.__qualname__ = T.__qualname__
+    _DistributedModelClass[T] = _Model
+    _DistributedModelNames.add(T.__name__)
+    return _Model
+
+
+Model = _DistributedModel(nn.Module)
+
+
+def distributed_model(model, sparse_as_dense_size=64, num_shards=None, override_method=True, explicit=False):
+    """Replace every ``nn.Embedding`` of `model` by a server-side ``Embedding``
+    (``sparse_as_dense`` when ``num_embeddings <= sparse_as_dense_size``) and add
+    ``save / save_weights / load_weights / save_as_original_model`` (exb.py:593-642).
+    Do not keep using the input model's old embedding modules afterwards."""
+    def convert(parent):
+        for cname, child in list(parent.named_children()):
+            if isinstance(child, nn.Embedding) and not isinstance(child, Embedding):
+                sad = child.num_embeddings <= sparse_as_dense_size
+                new = Embedding(child.num_embeddings, child.embedding_dim,
+                                embeddings_initializer={"category": "normal", "mean": 0.0, "stddev": 1.0},
+                                num_shards=num_shards, sparse_as_dense=sad, explicit=explicit,
+                                dtype=child.weight.dtype, name=cname)
+                setattr(parent, cname, new)
+            else:
+                convert(child)
+
+    if isinstance(model, nn.Embedding) and not isinstance(model, Embedding):
+        raise ValueError("wrap the nn.Embedding in a module")
+    convert(model)
+    ctx = get_context()
+    model.to(ctx.device)
+    if override_method:
+        model.__class__ = _DistributedModel(model.__class__)
+    return model
+
+
+# --------------------------------------------------------------------------- input pipeline
+def pulling(dataset, model, steps=None):
+    """EXPERIMENTAL: wrap an iterable of ``(inputs_dict, labels)`` batches so that the ids of
+    every server Embedding that is fed directly by exactly one input column are staged
+    on the device one batch ahead (exb.py:645-691). ``model.input_names`` (list of column
+    names aligned with the Embedding modules via ``layer_name``) selects the columns."""
+    emb_by_col = {}
+    for _, layer in _iter_embeddings(model):
+        if not layer.sparse_as_dense and layer.layer_name:
+            emb_by_col.setdefault(layer.layer_name, []).append(layer)
+    cols = {c: ls[0] for c, ls in emb_by_col.items() if len(ls) == 1}
+
+    def gen():
+        n = 0
+        for batch in dataset:
+            if steps is not None and n >= steps:
+                return
+            n += 1
+            if isinstance(batch, (tuple, list)) and isinstance(batch[0], dict):
+                feats = dict(batch[0])
+                for c, layer in cols.items():
+                    if c in feats:
+                        feats[c] = layer.variable.prefetch(feats[c], steps=steps)
+                yield (feats,) + tuple(batch[1:])
+            else:
+                yield batch
+
+    class _Pulling:
+        def __iter__(self):
+            # one-batch lookahead so the H2D copy of batch k+1 overlaps step k
+            it = gen()
+            try:
+                nxt = next(it)
+            except StopIteration:
+                return
+            for cur in it:
+                yield nxt
+                nxt = cur
+            yield nxt
+
+    return _Pulling()
+
+
+# --------------------------------------------------------------------------- host-tier persist (pmem experimental in the reference)
+def should_persist_server_model(model):
+    from .host_tier import should_persist
+    return should_persist(get_context())
+
+
+def persist_server_model(model, filepath, persist_pending_window):
+    from .host_tier import persist_model
+    persist_model(get_context(), filepath, persist_pending_window)
+
+
+def restore_server_model(model, filepath):
+    from .host_tier import restore_model
+    restore_model(get_context(), filepath)

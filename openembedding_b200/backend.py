@@ -1,0 +1,405 @@
+"""Sparse-table backends behind ``Context``.
+
+* ``CudaBackend`` -- the product: HBM shards + fused sm_100a kernels + NVLink peer memory
+  (``ops/sparse_engine.py``).
+* ``CpuBackend``  -- the plumbing/oracle configuration (BASELINE config 1: CPU + gloo):
+  shards live in ``libexb_core`` and ids / rows / grads travel with
+  ``all_to_all_single`` -- structurally the reference's pull/push RPC
+  (EmbeddingPullOperator.cpp:40-252, EmbeddingPushOperator.cpp:29-161) on torch
+  collectives.
+
+Both expose per-variable verbs (``pull`` / ``push`` / ``update``) and a fused multi-table
+group (``make_group``) used by the model zoo.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from .config import DTYPES, initializer_params, mix_seed, optimizer_params, optimizer_state_dim
+
+
+class VarMeta:
+    def __init__(self, variable_id, storage_id, vocab, dim, dtype, is_hash, shard_num, shard_base):
+        self.variable_id, self.storage_id = variable_id, storage_id
+        self.vocab, self.dim, self.dtype, self.is_hash = vocab, dim, dtype, is_hash
+        self.shard_num, self.shard_base = shard_num, shard_base
+        self.initializer = {"category": "constant", "value": 0.0}
+        self.optimizer = {"category": "default"}
+        self.handle = None     # backend specific
+
+
+def _owner_local(ids, meta, world):
+    shard = ids % meta.shard_num
+    owner = (meta.shard_base + shard) % world
+    return owner, ids // meta.shard_num
+
+
+# ======================================================================= CPU
+class CpuBackend:
+    name = "cpu"
+
+    def __init__(self, rank, world, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.lib = _native.core()
+        self.device = torch.device("cpu")
+        self.vars = []
+        self.counters = {"pull_indices": 0, "pull_unique": 0, "push_indices": 0}
+
+    # ---- variables
+    def create_variable(self, meta):
+        my_shard = (self.rank - meta.shard_base) % self.world
+        meta.my_shard = my_shard if my_shard < meta.shard_num else -1
+        sid = max(meta.my_shard, 0)
+        h = self.lib.exb_var_create(DTYPES[meta.dtype], meta.dim, 0 if meta.is_hash else meta.vocab, sid,
+                                    meta.shard_num, 1 if meta.is_hash else 0)
+        if not h:
+            raise ValueError("unsupported dtype for server variable: %s" % meta.dtype)
+        meta.handle = h
+        self.vars.append(meta)
+        return meta
+
+    def set_initializer(self, meta, cfg):
+        kind, p, seed = initializer_params(cfg)
+        self.lib.exb_var_set_initializer(meta.handle, kind, p[0], p[1], p[2], mix_seed(seed, meta.variable_id))
+
+    def set_optimizer(self, meta, cfg):
+        kind, p = optimizer_params(cfg)
+        self.lib.exb_var_set_optimizer(meta.handle, kind, (ctypes.c_double * 8)(*p), 8)
+
+    def _tdtype(self, meta):
+        return torch.float32 if meta.dtype == "float32" else torch.float64
+
+    # ---- exchange helpers
+    def _a2a(self, send, send_counts, width, dtype):
+        import torch.distributed as dist
+        counts_in = torch.tensor(send_counts, dtype=torch.int64)
+        counts_out = torch.empty(self.world, dtype=torch.int64)
+        dist.all_to_all_single(counts_out, counts_in, group=self.group)
+        recv_counts = counts_out.tolist()
+        recv = torch.empty((sum(recv_counts),) + ((width,) if width else ()), dtype=dtype)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts,
+                               input_split_sizes=list(send_counts), group=self.group)
+        return recv, recv_counts
+
+    def _a2a_known(self, send, send_counts, recv_counts, width, dtype):
+        import torch.distributed as dist
+        recv = torch.empty((sum(recv_counts),) + ((width,) if width else ()), dtype=dtype)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=list(recv_counts),
+                               input_split_sizes=list(send_counts), group=self.group)
+        return recv
+
+    # ---- verbs
+    def pull(self, meta, ids):
+        ids = ids.reshape(-1).to(torch.int64).contiguous()
+        n = ids.numel()
+        dt = self._tdtype(meta)
+        self.counters["pull_indices"] += n
+        # K1: dedup (reference client dedups per variable, EmbeddingPullOperator.cpp:60-84)
+        uniq, inverse = torch.unique(ids, return_inverse=True)
+        self.counters["pull_unique"] += uniq.numel()
+        if self.world == 1:
+            local = (uniq // meta.shard_num).contiguous()
+            rows = torch.empty((uniq.numel(), meta.dim), dtype=dt)
+            self.lib.exb_var_pull(meta.handle, local.data_ptr(), uniq.numel(), rows.data_ptr())
+            return rows[inverse]
+        owner, local = _owner_local(uniq, meta, self.world)
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=self.world).tolist()
+        req, recv_counts = self._a2a(local[order], send_counts, 0, torch.int64)
+        rows = torch.empty((req.numel(), meta.dim), dtype=dt)
+        if req.numel():
+            self.lib.exb_var_pull(meta.handle, req.data_ptr(), req.numel(), rows.data_ptr())
+        back = self._a2a_known(rows, recv_counts, send_counts, meta.dim, dt)
+        urows = torch.empty((uniq.numel(), meta.dim), dtype=dt)
+        urows[order] = back
+        return urows[inverse]
+
+    def push(self, meta, ids, grads):
+        ids = ids.reshape(-1).to(torch.int64).contiguous()
+        dt = self._tdtype(meta)
+        grads = grads.reshape(-1, meta.dim).to(dt).contiguous()
+        self.counters["push_indices"] += ids.numel()
+        # K4a: per-worker pre-reduce (sum grads, count duplicates; EmbeddingPushOperator.cpp:29-62)
+        uniq, inverse, counts = torch.unique(ids, return_inverse=True, return_counts=True)
+        g = torch.zeros((uniq.numel(), meta.dim), dtype=dt)
+        g.index_add_(0, inverse, grads)
+        counts = counts.to(torch.int64)
+        if self.world == 1:
+            local = (uniq // meta.shard_num).contiguous()
+            self.lib.exb_var_push(meta.handle, local.data_ptr(), uniq.numel(), g.data_ptr(), counts.data_ptr())
+            return
+        owner, local = _owner_local(uniq, meta, self.world)
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=self.world).tolist()
+        rid, recv_counts = self._a2a(local[order], send_counts, 0, torch.int64)
+        rg = self._a2a_known(g[order], send_counts, recv_counts, meta.dim, dt)
+        rc = self._a2a_known(counts[order], send_counts, recv_counts, 0, torch.int64)
+        if rid.numel():
+            self.lib.exb_var_push(meta.handle, rid.data_ptr(), rid.numel(), rg.data_ptr(), rc.data_ptr())
+
+    def update(self, metas=None):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)   # every worker's push has landed (the fake-gradient allreduce of the reference)
+        for meta in (metas or self.vars):
+            self.lib.exb_var_update(meta.handle)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    # ---- fused group (loop of per-variable verbs on CPU)
+    def make_group(self, metas, batch, feat_cols=None):
+        return _CpuGroup(self, metas, batch, feat_cols)
+
+    # ---- checkpoint side
+    def num_items(self, meta):
+        return int(self.lib.exb_var_num_items(meta.handle))
+
+    def state_dim(self, meta):
+        return optimizer_state_dim(meta.optimizer, meta.dim)
+
+    def iter_local_rows(self, meta, block_rows, with_state=True):
+        """yields (local_indices u64 ndarray, weights ndarray, states ndarray) of this rank's shard"""
+        if getattr(meta, "my_shard", 0) < 0:
+            return
+        cursor = ctypes.c_uint64(0)
+        np_dt = np.float32 if meta.dtype == "float32" else np.float64
+        sd = self.state_dim(meta)
+        while True:
+            idx = np.empty(block_rows, dtype=np.uint64)
+            n = int(self.lib.exb_var_read_indices(meta.handle, ctypes.byref(cursor), idx.ctypes.data, block_rows))
+            if n == 0:
+                break
+            idx = idx[:n]
+            w = np.empty((n, meta.dim), dtype=np_dt)
+            s = np.empty((n, sd), dtype=np_dt)
+            self.lib.exb_var_get_weights(meta.handle, idx.ctypes.data, n, w.ctypes.data,
+                                         s.ctypes.data if (with_state and sd) else None)
+            yield idx, w, (s if with_state else np.empty((n, 0), dtype=np_dt))
+
+    def load_rows(self, meta, global_ids, weights, states):
+        """rows whose owner is this rank are stored, the rest ignored (load re-shards)."""
+        ids = np.asarray(global_ids, dtype=np.uint64)
+        owner = (meta.shard_base + (ids % np.uint64(meta.shard_num)).astype(np.int64)) % self.world
+        m = owner == self.rank
+        if not m.any():
+            return
+        local = np.ascontiguousarray(ids[m] // np.uint64(meta.shard_num))
+        np_dt = np.float32 if meta.dtype == "float32" else np.float64
+        w = np.ascontiguousarray(np.asarray(weights)[m], dtype=np_dt)
+        sd = self.state_dim(meta)
+        st = np.asarray(states)
+        has_state = st.size > 0 and st.shape[1] == sd and sd > 0
+        s = np.ascontiguousarray(st[m], dtype=np_dt) if has_state else None
+        self.lib.exb_var_set_weights(meta.handle, local.ctypes.data, local.size, w.ctypes.data,
+                                     s.ctypes.data if s is not None else None,
+                                     sd * w.itemsize if s is not None else 0)
+
+    def clear(self, meta):
+        self.lib.exb_var_clear(meta.handle)
+
+    def table_kind(self, meta):
+        return "hash" if meta.is_hash else "array"
+
+    def shard_id(self, meta):
+        return getattr(meta, "my_shard", 0)
+
+    def synchronize(self):
+        pass
+
+    def close(self):
+        for m in self.vars:
+            if m.handle:
+                self.lib.exb_var_destroy(m.handle)
+                m.handle = None
+        self.vars = []
+
+
+class _CpuGroup:
+    def __init__(self, backend, metas, batch, feat_cols=None):
+        self.b, self.metas, self.B = backend, list(metas), batch
+        self.feat_cols = list(feat_cols) if feat_cols is not None else list(range(len(self.metas)))
+        self.dims = [m.dim for m in metas]
+        offs, o = [], 0
+        for d in self.dims:
+            offs.append(o)
+            o += d
+        self.feat_offsets, self.io_stride = offs, o
+
+    def feature_slices(self):
+        return [slice(o, o + d) for o, d in zip(self.feat_offsets, self.dims)]
+
+    def pull(self, ids):
+        out = torch.empty((ids.shape[0], self.io_stride), dtype=torch.float32)
+        for f, m in enumerate(self.metas):
+            out[:, self.feat_offsets[f]:self.feat_offsets[f] + m.dim] = self.b.pull(m, ids[:, self.feat_cols[f]]).to(torch.float32)
+        return out
+
+    def push_update(self, ids, grads):
+        for f, m in enumerate(self.metas):
+            self.b.push(m, ids[:, self.feat_cols[f]], grads[:, self.feat_offsets[f]:self.feat_offsets[f] + m.dim])
+        self.b.update(list(dict.fromkeys(self.metas)))
+
+
+# ====================================================================== CUDA
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, rank, world, device_index, group=None):
+        from .ops.sparse_engine import CudaEngine
+        self.rank, self.world, self.group = rank, world, group
+        self.engine = CudaEngine(device_index, rank, world)
+        self.device = self.engine.device
+        self.vars = []
+        self._plans = {}      # (variable_id, B) -> SparsePlan
+        self._pending = {}    # variable_id -> [(ids, grads)]
+        self.hash_reserve = 1 << 20
+
+    def create_variable(self, meta):
+        if meta.dtype != "float32":
+            raise ValueError("the CUDA engine stores float32 tables (use flags.device='cpu' for float64)")
+        t = self.engine.add_table(meta.dim, meta.vocab, meta.is_hash, capacity=self.hash_reserve,
+                                  shard_num=meta.shard_num, shard_base=meta.shard_base)
+        meta.handle = t
+        meta.allocated = False
+        self.vars.append(meta)
+        return meta
+
+    def set_initializer(self, meta, cfg):
+        if getattr(meta, "allocated", False):
+            # weights are materialised eagerly; a later initializer only affects rows
+            # that are (re)created from now on (hash misses, clear()).
+            pass
+        self.engine.set_initializer(meta.handle, cfg, meta.variable_id)
+
+    def set_optimizer(self, meta, cfg):
+        self.engine.set_optimizer(meta.handle, cfg)
+        if getattr(meta, "allocated", False):
+            self.engine.commit()
+
+    def ensure_allocated(self, metas=None):
+        """Collective: materialise not-yet-allocated tables and map them on every peer."""
+        todo = [m for m in (metas or self.vars) if not m.allocated]
+        if not todo:
+            return
+        for m in todo:
+            self.engine.alloc(m.handle)
+            m.allocated = True
+        self.engine.connect(self.group)
+
+    def _plan_for(self, meta, n):
+        cap = 1024
+        while cap < n:
+            cap *= 2
+        key = (meta.variable_id, cap)
+        plan = self._plans.get(key)
+        if plan is None:
+            self.ensure_allocated([meta])
+            plan = self.engine.make_plan([meta.handle], cap)
+            self.engine.connect(self.group)
+            self._plans[key] = plan
+        return plan
+
+    def pull(self, meta, ids):
+        ids = ids.reshape(-1, 1).to(device=self.device, dtype=torch.int64).contiguous()
+        plan = self._plan_for(meta, ids.shape[0])
+        out = plan.pull(ids)
+        return out[:, :meta.dim] if out.shape[1] != meta.dim else out
+
+    def push(self, meta, ids, grads):
+        ids = ids.reshape(-1, 1).to(device=self.device, dtype=torch.int64).contiguous()
+        grads = grads.reshape(-1, meta.dim).to(device=self.device, dtype=torch.float32)
+        self._pending.setdefault(meta.variable_id, []).append((ids, grads))
+
+    def update(self, metas=None):
+        for meta in (metas or self.vars):
+            pend = self._pending.pop(meta.variable_id, None)
+            if not pend:
+                continue
+            ids = torch.cat([p[0] for p in pend]) if len(pend) > 1 else pend[0][0]
+            g = torch.cat([p[1] for p in pend]) if len(pend) > 1 else pend[0][1]
+            plan = self._plan_for(meta, ids.shape[0])
+            if g.shape[1] != plan.io_stride:
+                gp = torch.zeros((g.shape[0], plan.io_stride), dtype=torch.float32, device=self.device)
+                gp[:, :meta.dim] = g
+                g = gp
+            plan.push_update(ids, g.contiguous())
+
+    def make_group(self, metas, batch, feat_cols=None):
+        self.ensure_allocated(list(metas))
+        plan = self.engine.make_plan([m.handle for m in metas], batch, feat_cols=feat_cols)
+        self.engine.connect(self.group)
+        return plan
+
+    # ---- checkpoint side
+    def num_items(self, meta):
+        self.ensure_allocated([meta])
+        if meta.is_hash:
+            return self.engine.table_size(meta.handle)
+        return int(self.engine.enumerate_ids(meta.handle).numel())
+
+    def state_dim(self, meta):
+        return optimizer_state_dim(meta.optimizer, meta.dim)
+
+    def shard_id(self, meta):
+        s = (self.rank - meta.shard_base) % self.world
+        return s if s < meta.shard_num else -1
+
+    def iter_local_rows(self, meta, block_rows, with_state=True):
+        self.ensure_allocated([meta])
+        if self.shard_id(meta) < 0:
+            return
+        ids = self.engine.enumerate_ids(meta.handle)   # K8: device key compaction
+        for i in range(0, ids.numel(), block_rows):
+            blk = ids[i:i + block_rows]
+            w, s = self.engine.gather_rows(meta.handle, blk, with_state=with_state)
+            local = (blk // meta.shard_num).cpu().numpy().astype(np.uint64)
+            yield local, w.cpu().numpy(), (s.cpu().numpy() if (with_state and s is not None)
+                                           else np.empty((blk.numel(), 0), dtype=np.float32))
+
+    def load_rows(self, meta, global_ids, weights, states):
+        self.ensure_allocated([meta])
+        ids = np.asarray(global_ids, dtype=np.uint64)
+        owner = (meta.shard_base + (ids % np.uint64(meta.shard_num)).astype(np.int64)) % self.world
+        m = owner == self.rank
+        if not m.any():
+            return
+        sd = self.state_dim(meta)
+        st = np.asarray(states)
+        has_state = st.size > 0 and st.shape[1] == sd and sd > 0
+        self.engine.scatter_rows(meta.handle, torch.from_numpy(ids[m].astype(np.int64)),
+                                 torch.from_numpy(np.ascontiguousarray(np.asarray(weights)[m], dtype=np.float32)),
+                                 torch.from_numpy(np.ascontiguousarray(st[m], dtype=np.float32)) if has_state else None)
+
+    def clear(self, meta):
+        if meta.allocated:
+            self.engine.clear_table(meta.handle)
+
+    def table_kind(self, meta):
+        return "hash" if meta.is_hash else "array"
+
+    def maybe_grow(self, load_factor=0.5):
+        """Collective: grow hash shards whose load exceeds `load_factor` (all ranks agree)."""
+        import torch.distributed as dist
+        grew = False
+        for meta in self.vars:
+            if not (meta.is_hash and meta.allocated):
+                continue
+            size = self.engine.table_size(meta.handle)
+            cap = self.engine.table_info(meta.handle)["rows"]
+            need = torch.tensor([1 if size > cap * load_factor else 0, cap], dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+            if int(need[0]):
+                self.engine.rehash(meta.handle, int(need[1]) * 2)
+                grew = True
+        if grew:
+            self.engine.connect(self.group)
+        return grew
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def close(self):
+        self.engine.close()

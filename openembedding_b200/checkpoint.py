@@ -1,0 +1,192 @@
+"""Server-model checkpoints in the reference's on-disk format (bit-compatible).
+
+Layout (writer openembedding/client/Model.cpp:89-108 and
+openembedding/server/EmbeddingDumpOperator.cpp:13-100, reader
+openembedding/server/EmbeddingLoadOperator.cpp:58-111)::
+
+    <path>/model_meta                      JSON, indent 4, {"model_sign","variables":[...],"version":"0.2"}
+    <path>/<storage_id>/model_<node>_<file>   per (shard, variable): header + blocks
+        header: u32 variable_id | i32 dtype | u64 dim | u64 vocab | u64 len + YAML config |
+                i32 shard_id | i32 shard_num | u64 state_line_size | u64 num_items
+        block : u64 n | u64 local_index[n] | T weights[n][dim] | byte states[n][state_line_size]
+        (global id = local_index * shard_num + shard_id)
+
+Loading re-shards: any rank count / shard count can read any checkpoint.
+
+Differences from the reference: there are no server processes, so ``save_model`` is a
+collective -- every rank streams its own HBM shard (device key compaction + row gather,
+kernel K8) into ``model_<rank>_<file>`` with the native writer in ``libexb_core``.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import _native
+from .config import DTYPE_NAMES, DTYPES, dump_variable_config, load_variable_config
+
+FORMAT_VERSION = "0.2"
+
+
+def block_rows(dim, itemsize, state_line_size):
+    """rows per block, EmbeddingVariable.cpp:84-87"""
+    return 1023 * 1024 // (dim * itemsize + state_line_size) + 1
+
+
+def model_meta_dict(ctx):
+    return {
+        "model_sign": ctx.model_sign(),
+        "variables": [{"datatype": m.dtype, "embedding_dim": m.dim, "vocabulary_size": m.vocab,
+                       "storage_name": str(m.storage_id)} for m in ctx.variables],
+        "version": FORMAT_VERSION,
+    }
+
+
+def read_model_meta(path):
+    with open(os.path.join(path, "model_meta")) as fh:
+        meta = json.load(fh)
+    ver = meta.get("version", "unknown")
+    if ver != FORMAT_VERSION:
+        raise ValueError("OpenEmbedding model format version is %s, current version is %s." % (ver, FORMAT_VERSION))
+    return meta
+
+
+def save_model(ctx, path, include_optimizer=True, num_files=None, persist=None):
+    """Collective. ``persist`` = dict(extra YAML keys) writes header-only records
+    (num_items = 0), the lightweight host-tier checkpoint (EmbeddingDumpOperator.cpp:65-77)."""
+    lib = _native.core()
+    null_sink = path.startswith("mem://null/")
+    num_files = num_files or int(ctx.env["server"]["server_dump_files"])
+    if not null_sink and ctx.rank == 0:
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "model_meta"), "w") as fh:
+            fh.write(json.dumps(model_meta_dict(ctx), indent=4))
+    ctx.barrier()
+    be = ctx.backend
+    be.synchronize()
+    for st in ctx.storages:
+        sdir = os.path.join(path, str(st.storage_id)) if not null_sink else path
+        if not null_sink:
+            os.makedirs(sdir, exist_ok=True)
+        writers = {}
+        for vid, meta in enumerate(st.variables):
+            shard_id = be.shard_id(meta)
+            if shard_id < 0:
+                continue
+            file_id = shard_id % num_files          # pico-ps operator/DumpOperator.h:73-76
+            if file_id not in writers:
+                fn = (sdir + "/model_%d_%d" % (ctx.rank, file_id)) if not null_sink else path
+                w = lib.exb_fw_open(fn.encode())
+                if not w:
+                    raise IOError("cannot open " + fn)
+                writers[file_id] = w
+            w = writers[file_id]
+            itemsize = 4 if meta.dtype == "float32" else 8
+            sls = be.state_dim(meta) * itemsize if include_optimizer else 0
+            n_items = 0 if persist is not None else be.num_items(meta)
+            cfg = dump_variable_config(be.table_kind(meta), n_items if persist is None else be.num_items(meta),
+                                       meta.optimizer, meta.initializer,
+                                       include_optimizer=include_optimizer, extra=persist).encode()
+            lib.exb_fw_header(w, vid, DTYPES[meta.dtype], meta.dim, meta.vocab, cfg, len(cfg),
+                              shard_id, meta.shard_num, sls, n_items)
+            if n_items:
+                written = 0
+                for idx, wts, sts in be.iter_local_rows(meta, block_rows(meta.dim, itemsize, sls),
+                                                        with_state=include_optimizer):
+                    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+                    wts = np.ascontiguousarray(wts)
+                    sts = np.ascontiguousarray(sts)
+                    lib.exb_fw_block(w, idx.size, idx.ctypes.data, wts.ctypes.data, wts.nbytes,
+                                     sts.ctypes.data if sts.nbytes else None, sts.nbytes if include_optimizer else 0)
+                    written += idx.size
+                if written != n_items:
+                    raise RuntimeError("dump: enumerated %d rows, header promised %d" % (written, n_items))
+        for w in writers.values():
+            lib.exb_fw_close(w)
+    ctx.barrier()
+
+
+def iter_shard_file(path):
+    """yield ('header', dict) then ('block', indices, weights, states) records of one file."""
+    lib = _native.core()
+    r = lib.exb_fr_open(path.encode())
+    if not r:
+        raise IOError("cannot open " + path)
+    try:
+        cfg = ctypes.create_string_buffer(1 << 20)
+        while True:
+            vid, dt = ctypes.c_uint32(), ctypes.c_int32()
+            dim, vocab, clen = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            sid, snum = ctypes.c_int32(), ctypes.c_int32()
+            sls, items = ctypes.c_uint64(), ctypes.c_uint64()
+            rc = lib.exb_fr_header(r, ctypes.byref(vid), ctypes.byref(dt), ctypes.byref(dim), ctypes.byref(vocab),
+                                   cfg, len(cfg), ctypes.byref(clen), ctypes.byref(sid), ctypes.byref(snum),
+                                   ctypes.byref(sls), ctypes.byref(items))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise IOError("corrupt shard file " + path)
+            hdr = {"variable_id": vid.value, "dtype": DTYPE_NAMES.get(dt.value, "unknown"), "dim": dim.value,
+                   "vocab": vocab.value, "config": cfg.raw[:clen.value].decode(), "shard_id": sid.value,
+                   "shard_num": snum.value, "state_line_size": sls.value, "num_items": items.value}
+            yield ("header", hdr)
+            np_dt = np.float32 if hdr["dtype"] == "float32" else np.float64
+            itemsize = np.dtype(np_dt).itemsize
+            done = 0
+            while done < hdr["num_items"]:
+                n = lib.exb_fr_block_size(r)
+                if n < 0:
+                    raise IOError("truncated shard file " + path)
+                idx = np.empty(n, dtype=np.uint64)
+                w = np.empty((n, hdr["dim"]), dtype=np_dt)
+                scols = hdr["state_line_size"] // itemsize
+                s = np.empty((n, scols), dtype=np_dt)
+                if lib.exb_fr_block(r, n, idx.ctypes.data, w.ctypes.data, w.nbytes,
+                                    s.ctypes.data if s.nbytes else None, s.nbytes) != 0:
+                    raise IOError("truncated shard file " + path)
+                gid = idx * np.uint64(hdr["shard_num"]) + np.uint64(hdr["shard_id"])
+                yield ("block", hdr, gid, w, s)
+                done += n
+    finally:
+        lib.exb_fr_close(r)
+
+
+def load_model(ctx, path, restore_config_only=False):
+    """Collective: every rank scans every file and keeps the rows it owns (re-shard)."""
+    meta = read_model_meta(path)
+    mine = model_meta_dict(ctx)["variables"]
+    if meta["variables"] != mine:
+        raise ValueError("model meta not match\n%s\n%s" % (json.dumps(meta["variables"], indent=4),
+                                                           json.dumps(mine, indent=4)))
+    be = ctx.backend
+    for m in ctx.variables:
+        be.clear(m)
+    for st in ctx.storages:
+        sdir = os.path.join(path, str(st.storage_id))
+        if not os.path.isdir(sdir):
+            continue
+        for fn in sorted(os.listdir(sdir)):
+            if not fn.startswith("model_"):
+                continue
+            for rec in iter_shard_file(os.path.join(sdir, fn)):
+                if rec[0] == "header":
+                    hdr = rec[1]
+                    var = st.variables[hdr["variable_id"]]
+                    cfg = load_variable_config(hdr["config"])
+                    # optimizer category change on load resets states (EmbeddingVariable.cpp:44-47)
+                    if "initializer" in cfg:
+                        ctx.set_initializer(var, cfg["initializer"])
+                    if "optimizer" in cfg and cfg["optimizer"] != var.optimizer:
+                        ctx.set_optimizer(var, cfg["optimizer"])
+                    continue
+                _, hdr, gid, w, s = rec
+                var = st.variables[hdr["variable_id"]]
+                be.load_rows(var, gid, w, s)
+    try:
+        sign = meta.get("model_sign", "")
+        ctx.loaded_model_sign = sign
+    except Exception:
+        pass
+    be.synchronize()
+    ctx.barrier()

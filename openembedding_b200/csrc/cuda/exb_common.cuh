@@ -1,0 +1,211 @@
+// exb_common.cuh -- device-side data model of the B200 sparse engine.
+//
+// The reference is a CPU parameter server: worker -> RPC -> server thread -> RPC -> worker
+// (SURVEY 3.2/3.3). Here every rank maps every peer's table slabs, inbox and flag words
+// (CUDA IPC over NVLink/NVSwitch) and the PS verbs are kernels:
+//   pull          = ids -> owner = id % W -> one-sided peer *loads* of rows     (K1+K2+K3)
+//   push + update = P2P *stores* of (id, grad) into the owner's inbox -> flag barrier
+//                   -> owner combines duplicates with atomics -> optimizer        (K4a+K4b)
+// `batch_id` gating of the reference (EmbeddingPullOperator.cpp:117-145) becomes a device
+// epoch counter exchanged through system-scope release/acquire flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "exb_math.h"
+
+#define EXB_MAX_PEERS 8
+#define EXB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+namespace exb {
+
+struct TableDev {
+    float* w[EXB_MAX_PEERS];                        // weight slab of every rank's shard (peer mapped)
+    const unsigned long long* keys[EXB_MAX_PEERS];  // hash keys of every rank's shard (hash tables)
+    float* state;                                   // local optimizer-state slab
+    unsigned* touched;                              // local bitmap of updated rows (array tables)
+    unsigned long long* size_ctr;                   // local number of occupied slots (hash tables)
+    unsigned long long rows;   // array: rows per shard = ceil(vocab / W); hash: capacity (pow2)
+    unsigned long long vocab;  // array: vocabulary; hash: 2^63
+    int dim, wstride, sstride, nslots, nscalars;
+    int is_hash, lpr, vec4;
+    int shard_num, shard_base;  // owner(id) = (shard_base + id % shard_num) % W, local row = id / shard_num
+    InitParams init;
+    OptParams opt;
+};
+
+struct PlanDev {
+    int F, B, PT, W, rank;
+    int num_tasks;          // sum_f ceil(B/32)
+    int io_stride;          // floats per row of out / grad
+    int ncols;              // id columns per batch row (several features may share one column)
+    const int* feat_pt;     // [F] feature -> plan-table
+    const int* feat_off;    // [F] column offset of the feature in out / grad rows
+    const int* feat_col;    // [F] id column of the feature
+    const int* task_prefix; // [F+1]
+    const int* pt_table;    // [PT] plan-table -> engine table id
+    const unsigned* pt_cap; // [PT] max entries one source can send for this table per step
+    const unsigned long long* pt_key_off;   // [PT] offset (u64 elements) inside one source block
+    const unsigned long long* pt_grad_off;  // [PT] offset (floats) inside one source block
+    unsigned long long src_key_stride, src_grad_stride;
+    unsigned long long* inbox_keys[EXB_MAX_PEERS];  // peer mapped, indexed by owner rank
+    float* inbox_grads[EXB_MAX_PEERS];
+    unsigned* inbox_cnt[EXB_MAX_PEERS];             // [W src][PT]
+    unsigned* send_cnt;                             // local [W owner][PT]
+    const unsigned long long* pt_map_off;           // [PT] offset into cmap arrays
+    const unsigned* pt_map_mask;                    // [PT] capacity-1 (pow2)
+    const unsigned long long* pt_acc_off;           // [PT] offset (floats) into acc
+    const unsigned long long* pt_ulist_off;         // [PT]
+    unsigned long long* cmap_keys;
+    unsigned* cmap_cnt;
+    float* acc;
+    unsigned* ulist;
+    unsigned* ucount;                               // [PT]
+    unsigned* flags[EXB_MAX_PEERS];                 // peer mapped [W]
+    unsigned* gbar;                                 // [0] arrive count, [1] generation
+    unsigned* epoch;                                // device-resident barrier epoch
+    int* status;                                    // 0 ok; else first error code
+    unsigned long long* stats;                      // [0] pull ids, [1] push ids, [2] unique rows updated
+};
+
+enum ExbStatus : int {
+    EXB_OK = 0,
+    EXB_ERR_TIMEOUT_GRID = 1,
+    EXB_ERR_TIMEOUT_PEER = 2,
+    EXB_ERR_HASH_FULL = 3,
+    EXB_ERR_INBOX_OVERFLOW = 4,
+    EXB_ERR_CMAP_FULL = 5,
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// fire-and-forget vector reduction (sm_90+): 4 fp32 adds in one L2 atomic transaction
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+// streaming 128-bit load that does not pollute L1 (rows are touched once per step)
+__device__ __forceinline__ float4 ld_stream_v4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+#define EXB_SPIN_TIMEOUT_NS 4000000000ull  // 4 s: a hung peer becomes an error code, not a hung box
+
+__device__ __forceinline__ void set_error(int* status, int code) { atomicCAS(status, 0, code); }
+
+// row sharding: the reference routes shard = id % global_shard_num, local = id / global_shard_num
+// (EmbeddingPullOperator.cpp:74-76) and places shards round-robin on servers
+// (WorkerContext.cpp:66-85); shard_base is that round-robin offset.
+__device__ __forceinline__ int owner_of(const TableDev& T, unsigned long long id, int W) {
+    return (int)(((unsigned)T.shard_base + (unsigned)(id % (unsigned)T.shard_num)) % (unsigned)W);
+}
+__device__ __forceinline__ unsigned long long local_row_of(const TableDev& T, unsigned long long id) {
+    return id / (unsigned)T.shard_num;
+}
+// shard index held by `rank` (>= shard_num means: this rank holds no shard of the table)
+__device__ __forceinline__ int shard_of_rank(const TableDev& T, int rank, int W) {
+    return (rank - T.shard_base % W + W) % W;
+}
+
+// Grid-wide barrier for a persistent kernel whose CTAs are all resident
+// (grid <= SMs * occupancy, enforced by the host). `master` runs on every thread of
+// CTA 0 while all other CTAs are parked -- this is where the cross-GPU flag exchange and
+// the count publication happen.
+template <class MasterFn>
+__device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, MasterFn master) {
+    if (sys_scope) __threadfence_system(); else __threadfence();
+    __syncthreads();
+    __shared__ unsigned s_gen;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            unsigned gen = ld_acquire_gpu_u32(&P.gbar[1]);
+            s_gen = gen;
+            atomicAdd(&P.gbar[0], 1u);
+            unsigned long long t0 = globaltimer_ns();
+            unsigned it = 0;
+            while (ld_acquire_gpu_u32(&P.gbar[0]) != gridDim.x) {
+                if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
+                    set_error(P.status, EXB_ERR_TIMEOUT_GRID);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        master();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            P.gbar[0] = 0;
+            __threadfence();
+            st_release_gpu_u32(&P.gbar[1], s_gen + 1);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            unsigned gen = ld_acquire_gpu_u32(&P.gbar[1]);
+            atomicAdd(&P.gbar[0], 1u);
+            unsigned long long t0 = globaltimer_ns();
+            unsigned it = 0;
+            while (ld_acquire_gpu_u32(&P.gbar[1]) == gen) {
+                if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
+                    set_error(P.status, EXB_ERR_TIMEOUT_GRID);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Cross-GPU barrier executed by CTA 0 (all its threads call this). Every rank writes its
+// new epoch into slot [rank] of every peer's flag array with a system-scope release and
+// then acquires its own array until all peers have reached the epoch.
+__device__ __forceinline__ void peer_barrier(const PlanDev& P) {
+    __threadfence_system();
+    __syncthreads();
+    unsigned e = *P.epoch + 1;
+    __syncthreads();
+    if ((int)threadIdx.x < P.W) {
+        st_release_sys_u32(&P.flags[threadIdx.x][P.rank], e);
+        unsigned long long t0 = globaltimer_ns();
+        unsigned it = 0;
+        while ((int)(ld_acquire_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
+            if ((++it & 255u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
+                set_error(P.status, EXB_ERR_TIMEOUT_PEER);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *P.epoch = e;
+    __threadfence_system();
+    __syncthreads();
+}
+
+}  // namespace exb

@@ -1,0 +1,160 @@
+"""Training step driver for the CTR zoo: streams, CUDA graph, end-to-end input pipeline.
+
+One step = H2D(ids, dense, labels) -> sparse pull (peer loads) -> dense fwd/bwd ->
+fused sparse push+update (P2P dispatch, combine, optimizer) || dense-gradient all-reduce
+(sum, like ``hvd.DistributedOptimizer(op=hvd.Sum)`` in the reference benchmark,
+test/benchmark/criteo_deepctr.py:262-263) -> dense Adagrad -> D2H(loss).
+
+The whole device part is captured in ONE CUDA graph (launch-bound at batch 4096); the
+input copy of step k+1 and the loss read of step k-1 overlap step k.
+"""
+import torch
+import torch.nn.functional as F
+
+from ..context import get_context
+
+
+class FlatAdagrad:
+    """tf.keras Adagrad (lr=0.001, initial_accumulator_value=0.1, eps=1e-7) over ONE flat
+    fp32 buffer that aliases every dense parameter -- 3 kernels regardless of the number
+    of parameters, graph capturable."""
+
+    def __init__(self, params, lr=0.001, initial_accumulator_value=0.1, eps=1e-7):
+        self.params = [p for p in params]
+        self.lr, self.eps = lr, eps
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.accum = torch.full((n,), initial_accumulator_value, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1).float())
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self):
+        g = self.grad
+        self.accum.addcmul_(g, g)
+        self.flat.addcdiv_(g, self.accum.sqrt().add_(self.eps), value=-self.lr)
+
+
+class Trainer:
+    def __init__(self, model, lr=0.001, use_graph=True, allreduce="auto"):
+        self.ctx = get_context()
+        self.model = model
+        self.device = self.ctx.device
+        self.world = self.ctx.world
+        self.opt = FlatAdagrad(model.dense_parameters(), lr=lr)
+        self.use_graph = use_graph and self.device.type == "cuda"
+        self.graph = None
+        self._static = None
+        self.allreduce = allreduce
+        self._ar = None
+        if self.world > 1 and self.device.type == "cuda":
+            from ..parallel.allreduce import make_allreduce
+            self._ar = make_allreduce(self.ctx, self.opt.grad, mode=allreduce)
+
+    # ---- one device step on given device tensors; returns loss tensor (0-dim, device)
+    def _device_step(self, ids, dense, labels):
+        self.opt.zero_grad()
+        logits = self.model(ids, dense)
+        loss = F.binary_cross_entropy_with_logits(logits, labels)
+        loss.backward()
+        if self.world > 1:
+            if self._ar is not None:
+                self._ar()
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self.opt.grad, group=self.ctx.group)
+        self.opt.step()
+        return loss.detach()
+
+    def step(self, ids, dense, labels):
+        """eager or graph-replayed step on device tensors"""
+        if not self.use_graph:
+            return self._device_step(ids, dense, labels)
+        if self.graph is None:
+            self._capture(ids, dense, labels)
+        s = self._static
+        if ids.data_ptr() != s["ids"].data_ptr():
+            s["ids"].copy_(ids, non_blocking=True)
+            s["dense"].copy_(dense, non_blocking=True)
+            s["labels"].copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return s["loss"]
+
+    def _capture(self, ids, dense, labels):
+        s = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):   # warm-up outside capture (allocator, cuBLAS handles, autotune)
+                self._device_step(s["ids"], s["dense"], s["labels"])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.ctx.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s["loss"] = self._device_step(s["ids"], s["dense"], s["labels"])
+        self.graph, self._static = g, s
+
+    def static_inputs(self):
+        return self._static
+
+    # ---- end-to-end: pinned host batch in, python float loss out (one step late)
+    def make_pipeline(self, batch, num_sparse, num_dense):
+        return _Pipeline(self, batch, num_sparse, num_dense)
+
+
+class _Pipeline:
+    """Double-buffered user-facing step: ``submit(host_ids, host_dense, host_labels)``
+    enqueues H2D on a copy stream, the graph on the compute stream and an async D2H of
+    the loss; ``losses()`` returns what has completed. Inputs must be pinned."""
+
+    def __init__(self, trainer, batch, num_sparse, num_dense):
+        self.t = trainer
+        dev = trainer.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.dev = [dict(ids=torch.zeros((batch, num_sparse), dtype=torch.int64, device=dev),
+                         dense=torch.zeros((batch, num_dense), dtype=torch.float32, device=dev),
+                         labels=torch.zeros((batch,), dtype=torch.float32, device=dev)) for _ in range(2)]
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        self.h2d_bytes = batch * num_sparse * 8 + batch * num_dense * 4 + batch * 4
+        self.d2h_bytes = 4
+
+    def submit(self, ids_h, dense_h, labels_h):
+        i = self.k & 1
+        cur = torch.cuda.current_stream(self.t.device)
+        if self.k >= 2:
+            self.copy_stream.wait_event(self.consumed[i])     # buffer i free again
+        with torch.cuda.stream(self.copy_stream):
+            d = self.dev[i]
+            d["ids"].copy_(ids_h, non_blocking=True)
+            d["dense"].copy_(dense_h, non_blocking=True)
+            d["labels"].copy_(labels_h, non_blocking=True)
+            self.copied[i].record(self.copy_stream)
+        cur.wait_event(self.copied[i])
+        if self.k >= 2:
+            self.done[i].synchronize()                        # loss_host[i] of step k-2 has landed
+        loss = self.t.step(self.dev[i]["ids"], self.dev[i]["dense"], self.dev[i]["labels"])
+        self.consumed[i].record(cur)
+        self.loss_host[i].copy_(loss, non_blocking=True)
+        self.done[i].record(cur)
+        self.k += 1
+
+    def last_loss(self):
+        i = (self.k - 1) & 1
+        self.done[i].synchronize()
+        return float(self.loss_host[i])

@@ -1,0 +1,306 @@
+"""Python face of the sm_100a sparse engine (``csrc/cuda/engine.cu``).
+
+``CudaEngine`` owns the table shards of one rank; ``SparsePlan`` is a fused
+multi-table lookup/update plan: ONE ``pull`` launch gathers every feature of a batch
+(peer loads over NVLink), ONE ``push_update`` launch dispatches, combines and applies
+the optimizer. The reference needs one RPC round per table per verb
+(openembedding/client/EmbeddingVariableHandle.cpp:106-155).
+"""
+import ctypes
+import os
+
+import torch
+
+from .. import _native
+from ..config import initializer_params, mix_seed, optimizer_params
+
+_STATUS_TEXT = {
+    0: "ok", 1: "grid barrier timeout", 2: "peer barrier timeout (a rank did not arrive)",
+    3: "hash table full (grow it)", 4: "inbox overflow", 5: "combine map full",
+}
+
+
+def cuda_available():
+    return torch.cuda.is_available()
+
+
+def _u64arr(n):
+    return (ctypes.c_uint64 * n)()
+
+
+class CudaEngine:
+    def __init__(self, device_index=0, rank=0, world=1, max_ctas=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CudaEngine needs a CUDA device; libexb_cuda has no CPU fallback")
+        self.lib = _native.cuda()
+        self.device_index = int(device_index)
+        self.device = torch.device("cuda", self.device_index)
+        self.rank, self.world = int(rank), int(world)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        self.h = self.lib.exb_engine_create(self.device_index, self.rank, self.world)
+        if not self.h:
+            raise RuntimeError("exb_engine_create: " + self.lib.exb_cuda_last_error().decode())
+        env_ctas = os.environ.get("EXB_MAX_CTAS")
+        if max_ctas is None and env_ctas:
+            max_ctas = int(env_ctas)
+        if max_ctas:
+            self.lib.exb_engine_set_max_ctas(self.h, int(max_ctas))
+        self.tables = []          # per table: dict(dim, vocab, is_hash, connected)
+        self.plans = []
+        self._sync_connected = self.world == 1
+        self._peer_open = []      # opened IPC pointers (closed at destroy)
+
+    # ---------------------------------------------------------------- tables
+    def add_table(self, dim, vocab, is_hash=False, capacity=0, shard_num=-1, shard_base=0):
+        t = self.lib.exb_table_add(self.h, int(bool(is_hash)), int(dim), int(vocab if not is_hash else 0),
+                                   int(capacity), int(shard_num), int(shard_base))
+        self.tables.append({"dim": int(dim), "vocab": int(vocab), "is_hash": bool(is_hash),
+                            "connected": self.world == 1, "allocated": False})
+        return t
+
+    def set_initializer(self, t, config, variable_id=0):
+        kind, p, seed = initializer_params(config)
+        _native.cuda_check(self.lib.exb_table_set_initializer(self.h, t, kind, p[0], p[1], p[2],
+                                                              mix_seed(seed, variable_id)), "set_initializer")
+
+    def set_optimizer(self, t, config):
+        kind, p = optimizer_params(config)
+        arr = (ctypes.c_double * 8)(*p)
+        _native.cuda_check(self.lib.exb_table_set_optimizer(self.h, t, kind, arr, 8), "set_optimizer")
+
+    def alloc(self, t):
+        _native.cuda_check(self.lib.exb_table_alloc(self.h, t), "table_alloc")
+        self.tables[t]["allocated"] = True
+
+    def table_info(self, t):
+        out = _u64arr(8)
+        self.lib.exb_table_info(self.h, t, out)
+        return {"w_ptr": out[0], "w_bytes": out[1], "keys_ptr": out[2], "keys_bytes": out[3],
+                "rows": out[4], "wstride": out[5], "sstride": out[6], "state_dim": out[7]}
+
+    def table_size(self, t):
+        out = _u64arr(1)
+        _native.cuda_check(self.lib.exb_table_size(self.h, t, out), "table_size")
+        return int(out[0])
+
+    def commit(self):
+        _native.cuda_check(self.lib.exb_engine_commit(self.h), "commit")
+
+    # ------------------------------------------------------- peer connection
+    def _export(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        _native.cuda_check(self.lib.exb_ipc_get_handle(ptr, buf), "ipc_get_handle")
+        return buf.raw
+
+    def _open(self, raw):
+        p = self.lib.exb_ipc_open_handle(ctypes.create_string_buffer(raw, 64))
+        if not p:
+            raise RuntimeError("cudaIpcOpenMemHandle: " + self.lib.exb_cuda_last_error().decode())
+        self._peer_open.append(p)
+        return p
+
+    def connect(self, group=None):
+        """Collective: exchange CUDA-IPC handles of everything not yet peer-mapped."""
+        if self.world == 1:
+            self.commit()
+            return
+        import torch.distributed as dist
+        mine = {"sync": None, "tables": {}, "plans": {}}
+        if not self._sync_connected:
+            mine["sync"] = self._export(self.lib.exb_engine_sync_ptr(self.h))
+        for t, meta in enumerate(self.tables):
+            if meta["allocated"] and not meta["connected"]:
+                info = self.table_info(t)
+                mine["tables"][t] = (self._export(info["w_ptr"]),
+                                     self._export(info["keys_ptr"]) if info["keys_ptr"] else None)
+        for i, plan in enumerate(self.plans):
+            if not plan.connected:
+                mine["plans"][i] = self._export(plan.inbox_info()[0])
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=group)
+        for r, theirs in enumerate(gathered):
+            if r == self.rank:
+                continue
+            if theirs["sync"] is not None:
+                self.lib.exb_engine_set_peer_sync(self.h, r, self._open(theirs["sync"]))
+            for t, (wh, kh) in theirs["tables"].items():
+                self.lib.exb_table_set_peer(self.h, t, r, self._open(wh), self._open(kh) if kh else 0)
+            for i, ih in theirs["plans"].items():
+                self.lib.exb_plan_set_peer_inbox(self.plans[i].h, r, self._open(ih))
+        self._sync_connected = True
+        for meta in self.tables:
+            if meta["allocated"]:
+                meta["connected"] = True
+        self.commit()
+        for plan in self.plans:
+            if not plan.connected:
+                _native.cuda_check(self.lib.exb_plan_commit(plan.h), "plan_commit")
+                plan.connected = True
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_local(engines):
+        """Wire several engines living in ONE process on ONE device as virtual ranks
+        (test harness for the multi-rank protocol without multiple GPUs)."""
+        W = len(engines)
+        for e in engines:
+            assert e.world == W
+        for a in engines:
+            for b in engines:
+                if a is b:
+                    continue
+                a.lib.exb_engine_set_peer_sync(a.h, b.rank, b.lib.exb_engine_sync_ptr(b.h))
+                for t in range(len(a.tables)):
+                    info = b.table_info(t)
+                    a.lib.exb_table_set_peer(a.h, t, b.rank, info["w_ptr"], info["keys_ptr"])
+                for i, plan in enumerate(a.plans):
+                    a.lib.exb_plan_set_peer_inbox(plan.h, b.rank, b.plans[i].inbox_info()[0])
+        for e in engines:
+            e._sync_connected = True
+            for meta in e.tables:
+                meta["connected"] = True
+            e.commit()
+            for plan in e.plans:
+                _native.cuda_check(e.lib.exb_plan_commit(plan.h), "plan_commit")
+                plan.connected = True
+
+    # ---------------------------------------------------------------- plans
+    def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None):
+        return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols)
+
+    # --------------------------------------------------------------- status
+    def status(self):
+        st = ctypes.c_int32(0)
+        stats = _u64arr(3)
+        _native.cuda_check(self.lib.exb_engine_status(self.h, ctypes.byref(st), stats), "status")
+        return int(st.value), {"pull_indices": int(stats[0]), "push_indices": int(stats[1]),
+                               "update_unique": int(stats[2])}
+
+    def check(self):
+        code, _ = self.status()
+        if code != 0:
+            self.lib.exb_engine_reset_status(self.h)
+            raise RuntimeError("sparse engine error %d: %s" % (code, _STATUS_TEXT.get(code, "?")))
+
+    # ---------------------------------------------- checkpoint-side row access
+    def enumerate_ids(self, t):
+        """Global ids of all materialised local rows, sorted (device tensor, int64)."""
+        info = self.table_info(t)
+        cap = int(info["rows"])
+        out = torch.empty(max(cap, 1), dtype=torch.int64, device=self.device)
+        n = _u64arr(1)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _native.cuda_check(self.lib.exb_table_enumerate(self.h, t, out.data_ptr(), cap, n, s), "enumerate")
+        return torch.sort(out[: int(n[0])])[0]
+
+    def gather_rows(self, t, ids, with_state=True):
+        info = self.table_info(t)
+        dim = self.tables[t]["dim"]
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        n = ids.numel()
+        w = torch.empty((n, dim), dtype=torch.float32, device=self.device)
+        sd = int(info["state_dim"])
+        s = torch.empty((n, sd), dtype=torch.float32, device=self.device) if with_state else None
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _native.cuda_check(self.lib.exb_table_gather(self.h, t, ids.data_ptr(), n, w.data_ptr(),
+                                                     s.data_ptr() if (with_state and sd) else 0, st), "gather")
+        return w, s
+
+    def scatter_rows(self, t, ids, weights, states=None):
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        w = weights.to(device=self.device, dtype=torch.float32).contiguous()
+        s = states.to(device=self.device, dtype=torch.float32).contiguous() if states is not None and states.numel() else None
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _native.cuda_check(self.lib.exb_table_scatter(self.h, t, ids.data_ptr(), ids.numel(), w.data_ptr(),
+                                                      s.data_ptr() if s is not None else 0, st), "scatter")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def clear_table(self, t):
+        _native.cuda_check(self.lib.exb_table_clear(self.h, t), "clear")
+
+    def rehash(self, t, new_capacity):
+        _native.cuda_check(self.lib.exb_table_rehash(self.h, t, int(new_capacity)), "rehash")
+        self.tables[t]["connected"] = self.world == 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in self.plans:
+                p.close()
+            for ptr in self._peer_open:
+                self.lib.exb_ipc_close_handle(ptr)
+            self._peer_open = []
+            self.lib.exb_engine_destroy(self.h)
+            self.h = None
+
+
+class SparsePlan:
+    """Fused lookup/update over F features of one batch (ids ``[B, F]`` int64)."""
+
+    def __init__(self, engine, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None):
+        self.e = engine
+        self.lib = engine.lib
+        self.F = len(feat_tables)
+        self.B = int(batch)
+        self.feat_tables = [int(t) for t in feat_tables]
+        widths = [int(engine.table_info(t)["wstride"]) for t in self.feat_tables]
+        self.dims = [engine.tables[t]["dim"] for t in self.feat_tables]
+        if feat_offsets is None:
+            feat_offsets, o = [], 0
+            for w in widths:
+                o = (o + 3) // 4 * 4 if w % 4 == 0 else o
+                feat_offsets.append(o)
+                o += w
+            total = (o + 3) // 4 * 4
+        else:
+            total = max(o + w for o, w in zip(feat_offsets, widths))
+        self.feat_offsets = [int(o) for o in feat_offsets]
+        self.io_stride = int(io_stride) if io_stride is not None else total
+        self.feat_cols = [int(c) for c in (feat_cols if feat_cols is not None else range(self.F))]
+        self.ncols = max(self.feat_cols) + 1
+        ft = (ctypes.c_int32 * self.F)(*self.feat_tables)
+        fo = (ctypes.c_int32 * self.F)(*self.feat_offsets)
+        fc = (ctypes.c_int32 * self.F)(*self.feat_cols)
+        self.h = self.lib.exb_plan_create(engine.h, self.F, ft, fo, fc, self.ncols, self.B, self.io_stride)
+        if not self.h:
+            raise RuntimeError("exb_plan_create: " + self.lib.exb_cuda_last_error().decode())
+        self.connected = engine.world == 1
+        engine.plans.append(self)
+        if engine.world == 1:
+            engine.commit()
+            _native.cuda_check(self.lib.exb_plan_commit(self.h), "plan_commit")
+
+    def inbox_info(self):
+        out = _u64arr(2)
+        self.lib.exb_plan_inbox_info(self.h, out)
+        return int(out[0]), int(out[1])
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.e.device).cuda_stream
+
+    def pull(self, ids, out=None):
+        """ids [n, ncols] int64 (cuda, contiguous) -> out [n, io_stride] fp32."""
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape[1] == self.ncols
+        n = ids.shape[0]
+        if out is None:
+            out = torch.empty((n, self.io_stride), dtype=torch.float32, device=ids.device)
+        _native.cuda_check(self.lib.exb_pull(self.h, ids.data_ptr(), out.data_ptr(), n, self._stream()), "pull")
+        return out
+
+    def push_update(self, ids, grads):
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous()
+        assert grads.dtype == torch.float32 and grads.is_contiguous() and grads.shape[1] == self.io_stride
+        _native.cuda_check(self.lib.exb_push_update(self.h, ids.data_ptr(), grads.data_ptr(), ids.shape[0],
+                                                    self._stream()), "push_update")
+
+    def grid(self):
+        return self.lib.exb_plan_grid(self.h, 0), self.lib.exb_plan_grid(self.h, 1)
+
+    def feature_slices(self):
+        return [slice(o, o + d) for o, d in zip(self.feat_offsets, self.dims)]
+
+    def close(self):
+        if self.h:
+            self.lib.exb_plan_destroy(self.h)
+            self.h = None
