@@ -222,6 +222,7 @@ def main():
             "gpu_launches": own_kernels_per_step * a.steps,
             "native_libs": {"cuda": _native.cuda_loaded()},
             "final_loss": loss_val, "e2e_final_loss": e2e_loss,
+            "push_update_phases_us": ctx.backend.engine.status()[1].get("last_push_update_us"),
         }
         print(json.dumps(line))
     if world > 1:

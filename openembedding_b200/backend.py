@@ -149,7 +149,7 @@ class CpuBackend:
             dist.barrier(group=self.group)
 
     # ---- fused group (loop of per-variable verbs on CPU)
-    def make_group(self, metas, batch, feat_cols=None):
+    def make_group(self, metas, batch, feat_cols=None, ncols=None):
         return _CpuGroup(self, metas, batch, feat_cols)
 
     # ---- checkpoint side
@@ -326,9 +326,9 @@ class CudaBackend:
                 g = gp
             plan.push_update(ids, g.contiguous())
 
-    def make_group(self, metas, batch, feat_cols=None):
+    def make_group(self, metas, batch, feat_cols=None, ncols=None):
         self.ensure_allocated(list(metas))
-        plan = self.engine.make_plan([m.handle for m in metas], batch, feat_cols=feat_cols)
+        plan = self.engine.make_plan([m.handle for m in metas], batch, feat_cols=feat_cols, ncols=ncols)
         self.engine.connect(self.group)
         return plan
 

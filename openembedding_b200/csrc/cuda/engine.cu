@@ -6,6 +6,7 @@
 // Connection/WorkerContext/EmbeddingVariableHandle client runtime and the
 // ps::Server request loop (openembedding/client/*.cpp, pico-ps/service/Service.cpp).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,7 @@ struct Plan {
     size_t inbox_bytes = 0, inbox_grads_off = 0, inbox_cnt_off = 0;
     char* work = nullptr;   // send_cnt | ucount | cmap_keys | cmap_cnt | ulist | acc
     int grid_pull = 1, grid_push = 1;
+    size_t smem_pull = 0, smem_push = 0;
 };
 
 int pow2_ceil_int(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -79,7 +81,7 @@ __global__ void array_fill_weights_kernel(TableDev T, int rank, int W) {
         unsigned long long id = row * (unsigned long long)T.shard_num + shard_of_rank(T, rank, W);
         float* wrow = T.w[rank] + row * T.wstride;
         if (T.vec4) {
-            *reinterpret_cast<float4*>(wrow + c) = init_block_masked(T.init, id, c, T.dim);
+            *reinterpret_cast<float4*>(wrow + c) = init_block_masked(&T.init, id, c, T.dim);
         } else {
             float t[4];
             InitGen<float>::block4(T.init, id, 0u, t);
@@ -343,12 +345,12 @@ uint64_t exb_engine_sync_bytes() { return SYNC_BYTES; }
 void exb_engine_set_peer_sync(void* h, int peer, uint64_t ptr) { ((Engine*)h)->sync_peer[peer] = (char*)ptr; }
 
 // returns 0 and the error status word (device sync!)
-int exb_engine_status(void* h, int* status, uint64_t* stats3) {
+int exb_engine_status(void* h, int* status, uint64_t* stats16) {
     Engine* e = (Engine*)h;
     CK(cudaSetDevice(e->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(status, e->sync_local + OFF_STATUS, 4, cudaMemcpyDeviceToHost));
-    if (stats3) CK(cudaMemcpy(stats3, e->sync_local + OFF_STATS, 24, cudaMemcpyDeviceToHost));
+    if (stats16) CK(cudaMemcpy(stats16, e->sync_local + OFF_STATS, 256, cudaMemcpyDeviceToHost));
     return 0;
 }
 int exb_engine_reset_status(void* h) {
@@ -668,7 +670,7 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     // ---- local work: send_cnt | ucount | cmap_keys | cmap_cnt | ulist | acc
     size_t woff = 0;
     auto wtake = [&](size_t bytes) { size_t o = woff; woff = align_up(woff + bytes, 256); return o; };
-    size_t o_send = wtake((size_t)W * PT * 4), o_ucount = wtake(PT * 4), o_ckeys = wtake(mo * 8), o_ccnt = wtake(mo * 4),
+    size_t o_send = wtake((size_t)W * PT * 4 * EXB_CTR_STRIDE), o_ucount = wtake((size_t)PT * 4 * EXB_CTR_STRIDE), o_ckeys = wtake(mo * 8), o_ccnt = wtake(mo * 4),
            o_ulist = wtake(uo * 4), o_acc = wtake(ao * 4);
     CKP(cudaMalloc(&p->work, woff));
     CKP(cudaMemset(p->work, 0, woff));
@@ -684,13 +686,24 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     d.status = (int*)(e->sync_local + OFF_STATUS);
     d.stats = (unsigned long long*)(e->sync_local + OFF_STATS);
     // ---- launch geometry: persistent push kernel must be fully resident
+    p->smem_pull = exb_smem_total(PT, F, false);
+    p->smem_push = exb_smem_total(PT, F, true);
+    {
+        const char* eb = getenv("EXB_BULK");
+        d.use_bulk = (eb && eb[0] == '0') ? 0 : 1;
+    }
+    cudaFuncSetAttribute(exb_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(exb_push_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_push_update_kernel, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_push_update_kernel, 256, p->smem_push);
     if (occ < 1) occ = 1;
-    int resident = e->sms * std::min(occ, 2);
+    int resident = e->sms * std::min(occ, 4);
     int want = std::max(1, (d.num_tasks * std::max(1, W / 2 + 1) + 7) / 8);
     p->grid_push = std::min(resident, want);
-    p->grid_pull = std::max(1, std::min(e->sms * 8, (d.num_tasks + 7) / 8));
+    int occ_pull = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pull, exb_pull_kernel, 256, p->smem_pull);
+    if (occ_pull < 1) occ_pull = 1;
+    p->grid_pull = std::max(1, std::min(e->sms * occ_pull, (d.num_tasks + 7) / 8));
     if (e->max_ctas > 0) { p->grid_push = std::min(p->grid_push, e->max_ctas); p->grid_pull = std::min(p->grid_pull, e->max_ctas); }
     CKP(cudaDeviceSynchronize());
     return p;
@@ -731,7 +744,7 @@ int exb_pull(void* ph, uint64_t ids, uint64_t out, int n_rows, uint64_t stream) 
     Plan* p = (Plan*)ph;
     Engine* e = p->e;
     if (n_rows > p->d.B) return fail_msg("pull: n_rows exceeds plan batch");
-    exb_pull_kernel<<<p->grid_pull, 256, 0, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
+    exb_pull_kernel<<<p->grid_pull, 256, p->smem_pull, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
                                                                     (float*)out, n_rows);
     CK(cudaGetLastError());
     return 0;
@@ -740,7 +753,7 @@ int exb_push_update(void* ph, uint64_t ids, uint64_t grads, int n_rows, uint64_t
     Plan* p = (Plan*)ph;
     Engine* e = p->e;
     if (n_rows > p->d.B) return fail_msg("push: n_rows exceeds plan batch");
-    exb_push_update_kernel<<<p->grid_push, 256, 0, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
+    exb_push_update_kernel<<<p->grid_push, 256, p->smem_push, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
                                                                            (const float*)grads, n_rows);
     CK(cudaGetLastError());
     return 0;

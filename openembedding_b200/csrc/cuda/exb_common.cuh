@@ -39,6 +39,8 @@ struct PlanDev {
     int num_tasks;          // sum_f ceil(B/32)
     int io_stride;          // floats per row of out / grad
     int ncols;              // id columns per batch row (several features may share one column)
+    int use_bulk;           // 1: rows move through shared memory with cp.async.bulk (UBLKCP)
+    int _pad1;
     const int* feat_pt;     // [F] feature -> plan-table
     const int* feat_off;    // [F] column offset of the feature in out / grad rows
     const int* feat_col;    // [F] id column of the feature
@@ -135,6 +137,22 @@ __device__ __forceinline__ int shard_of_rank(const TableDev& T, int rank, int W)
     return (rank - T.shard_base % W + W) % W;
 }
 
+// Polling loads are RELAXED (no per-iteration L1 invalidate: `ld.acquire` lowers to
+// LDG + CCTL.IVALL, and a spinning thread would keep flushing the L1 that co-resident
+// CTAs are still working out of); one acquire fence is issued after the loop exits.
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 // Grid-wide barrier for a persistent kernel whose CTAs are all resident
 // (grid <= SMs * occupancy, enforced by the host). `master` runs on every thread of
 // CTA 0 while all other CTAs are parked -- this is where the cross-GPU flag exchange and
@@ -146,17 +164,19 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
     __shared__ unsigned s_gen;
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
-            unsigned gen = ld_acquire_gpu_u32(&P.gbar[1]);
+            unsigned gen = ld_relaxed_gpu_u32(&P.gbar[1]);
             s_gen = gen;
             atomicAdd(&P.gbar[0], 1u);
             unsigned long long t0 = globaltimer_ns();
             unsigned it = 0;
-            while (ld_acquire_gpu_u32(&P.gbar[0]) != gridDim.x) {
+            while (ld_relaxed_gpu_u32(&P.gbar[0]) != gridDim.x) {
+                __nanosleep(32);
                 if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                     set_error(P.status, EXB_ERR_TIMEOUT_GRID);
                     break;
                 }
             }
+            fence_acq_rel_gpu();
         }
         __syncthreads();
         master();
@@ -168,16 +188,19 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
         }
     } else {
         if (threadIdx.x == 0) {
-            unsigned gen = ld_acquire_gpu_u32(&P.gbar[1]);
+            unsigned gen = ld_relaxed_gpu_u32(&P.gbar[1]);
+            __threadfence();
             atomicAdd(&P.gbar[0], 1u);
             unsigned long long t0 = globaltimer_ns();
             unsigned it = 0;
-            while (ld_acquire_gpu_u32(&P.gbar[1]) == gen) {
+            while (ld_relaxed_gpu_u32(&P.gbar[1]) == gen) {
+                __nanosleep(64);
                 if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                     set_error(P.status, EXB_ERR_TIMEOUT_GRID);
                     break;
                 }
             }
+            fence_acq_rel_gpu();
         }
     }
     __syncthreads();
@@ -185,25 +208,26 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
 
 // Cross-GPU barrier executed by CTA 0 (all its threads call this). Every rank writes its
 // new epoch into slot [rank] of every peer's flag array with a system-scope release and
-// then acquires its own array until all peers have reached the epoch.
+// then polls its own array until all peers have reached the epoch (acquire fence after).
 __device__ __forceinline__ void peer_barrier(const PlanDev& P) {
     __threadfence_system();
     __syncthreads();
-    unsigned e = *P.epoch + 1;
+    unsigned e = *(volatile unsigned*)P.epoch + 1;
     __syncthreads();
     if ((int)threadIdx.x < P.W) {
         st_release_sys_u32(&P.flags[threadIdx.x][P.rank], e);
         unsigned long long t0 = globaltimer_ns();
         unsigned it = 0;
-        while ((int)(ld_acquire_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
+        while ((int)(ld_relaxed_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
             if ((++it & 255u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                 set_error(P.status, EXB_ERR_TIMEOUT_PEER);
                 break;
             }
         }
+        fence_acq_rel_sys();
     }
     __syncthreads();
-    if (threadIdx.x == 0) *P.epoch = e;
+    if (threadIdx.x == 0) *(volatile unsigned*)P.epoch = e;
     __threadfence_system();
     __syncthreads();
 }

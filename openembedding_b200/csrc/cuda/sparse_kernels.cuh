@@ -1,6 +1,6 @@
 // sparse_kernels.cuh -- the two fused sparse hot paths of the engine (sm_100a).
 //
-//  exb_pull_kernel        K1+K2+K3 of SURVEY 2.5: bucketize by owner (id % W), one-sided
+//  exb_pull_kernel        K1+K2+K3 of SURVEY 2.5: bucketize by owner (id % S), one-sided
 //                         peer loads of the rows over NVLink (array: direct address, hash:
 //                         probe in the owner's key slab), scatter into request order.
 //                         Missing hash rows are answered with the Philox initial value.
@@ -15,14 +15,92 @@
 //                   new rows) -> optimizer functor -> write back, reset map entry
 //     B3            cross-GPU "update done" barrier (next pull may read any shard)
 //
+// Both kernels are latency-bound gather/scatter machines, so: (1) every descriptor the
+// inner loops touch (table structs, plan index arrays) is staged in shared memory once
+// per CTA, (2) each lane group issues a batch of independent 128-bit loads before it
+// consumes any of them (memory-level parallelism instead of occupancy), (3) barriers
+// poll with relaxed loads.
+//
 // Reference semantics preserved: gradients of duplicate ids are SUMMED, counts are
 // summed (MpscGradientReducer.h:30-53); rows are materialised at their first update.
 #pragma once
 #include "exb_common.cuh"
+#include "bulk_rows.cuh"
 
 namespace exb {
 
-__device__ __forceinline__ int find_segment(const int* __restrict__ prefix, int n, int task) {
+#define EXB_MAX_SEG 1024  // max W*PT segments of the combine phase
+#define EXB_MAX_PT 128
+
+struct SmemView {
+    TableDev* tab;                 // [PT] copies of the plan's table descriptors
+    unsigned long long* key_off;   // [PT]
+    unsigned long long* grad_off;  // [PT]
+    unsigned long long* map_off;   // [PT]
+    unsigned long long* acc_off;   // [PT]
+    unsigned long long* ulist_off; // [PT]
+    unsigned* cap;                 // [PT]
+    unsigned* map_mask;            // [PT]
+    int* task_prefix;              // [F+1]
+    int* feat_pt;                  // [F]
+    int* feat_off;                 // [F]
+    int* feat_col;                 // [F]
+    int* seg_prefix;               // [EXB_MAX_SEG+1] (push kernel only)
+};
+
+__host__ __device__ inline size_t exb_smem_bytes(int PT, int F, bool push) {
+    size_t b = (size_t)PT * sizeof(TableDev) + (size_t)PT * 8 * 5 + (size_t)PT * 4 * 2 +
+               (size_t)(F + 1) * 4 + (size_t)F * 4 * 3;
+    if (push) b += (EXB_MAX_SEG + 1) * 4;
+    return (b + 127) & ~(size_t)127;
+}
+// total dynamic shared memory of a 256-thread CTA: staged descriptors | per-warp row buffers |
+// (push: per-warp metadata) | per-warp mbarriers
+__host__ __device__ inline size_t exb_smem_total(int PT, int F, bool push) {
+    size_t b = exb_smem_bytes(PT, F, push);
+    b += 8 * (size_t)(push ? EXB_APPLY_WARP_BUF : EXB_PULL_WARP_BUF);
+    if (push) b += 8 * sizeof(WarpMeta);
+    b += 8 * 8;
+    return b;
+}
+
+__device__ __forceinline__ SmemView stage_plan(const TableDev* __restrict__ tables, const PlanDev& P,
+                                               unsigned char* smem) {
+    SmemView S;
+    const int PT = P.PT, F = P.F;
+    unsigned char* p = smem;
+    S.tab = (TableDev*)p; p += (size_t)PT * sizeof(TableDev);
+    S.key_off = (unsigned long long*)p; p += PT * 8;
+    S.grad_off = (unsigned long long*)p; p += PT * 8;
+    S.map_off = (unsigned long long*)p; p += PT * 8;
+    S.acc_off = (unsigned long long*)p; p += PT * 8;
+    S.ulist_off = (unsigned long long*)p; p += PT * 8;
+    S.cap = (unsigned*)p; p += PT * 4;
+    S.map_mask = (unsigned*)p; p += PT * 4;
+    S.task_prefix = (int*)p; p += (F + 1) * 4;
+    S.feat_pt = (int*)p; p += F * 4;
+    S.feat_off = (int*)p; p += F * 4;
+    S.feat_col = (int*)p; p += F * 4;
+    S.seg_prefix = (int*)p;
+    constexpr int TW = sizeof(TableDev) / 4;
+    for (int i = threadIdx.x; i < PT * TW; i += blockDim.x) {
+        int pt = i / TW, w = i - pt * TW;
+        ((unsigned*)S.tab)[i] = ((const unsigned*)(tables + P.pt_table[pt]))[w];
+    }
+    for (int i = threadIdx.x; i < PT; i += blockDim.x) {
+        S.key_off[i] = P.pt_key_off[i]; S.grad_off[i] = P.pt_grad_off[i]; S.map_off[i] = P.pt_map_off[i];
+        S.acc_off[i] = P.pt_acc_off[i]; S.ulist_off[i] = P.pt_ulist_off[i];
+        S.cap[i] = P.pt_cap[i]; S.map_mask[i] = P.pt_map_mask[i];
+    }
+    for (int i = threadIdx.x; i <= F; i += blockDim.x) S.task_prefix[i] = P.task_prefix[i];
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        S.feat_pt[i] = P.feat_pt[i]; S.feat_off[i] = P.feat_off[i]; S.feat_col[i] = P.feat_col[i];
+    }
+    __syncthreads();
+    return S;
+}
+
+__device__ __forceinline__ int find_segment(const int* prefix, int n, int task) {
     int lo = 0, hi = n;  // prefix[lo] <= task < prefix[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -31,16 +109,23 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ prefix, int 
     return lo;
 }
 
-__device__ __forceinline__ float4 init_block_masked(const InitParams& I, unsigned long long id,
-                                                    int c, int dim) {
+// initializer values of elements c..c+3 of row `id` (cold path: kept out of line so the hot
+// gather loops do not carry Philox in registers)
+__device__ __noinline__ float4 init_block_masked(const InitParams* I, unsigned long long id, int c,
+                                                 int dim) {
     float t[4];
-    InitGen<float>::block4(I, id, (uint32_t)(c >> 2), t);
+    InitGen<float>::block4(*I, id, (uint32_t)(c >> 2), t);
     float4 v;
     v.x = (c + 0 < dim) ? t[0] : 0.f;
     v.y = (c + 1 < dim) ? t[1] : 0.f;
     v.z = (c + 2 < dim) ? t[2] : 0.f;
     v.w = (c + 3 < dim) ? t[3] : 0.f;
     return v;
+}
+__device__ __noinline__ float init_scalar(const InitParams* I, unsigned long long id, int c) {
+    float t[4];
+    InitGen<float>::block4(*I, id, (uint32_t)(c >> 2), t);
+    return t[c & 3];
 }
 
 // ------------------------------------------------------------------ pull
@@ -50,63 +135,83 @@ __device__ __forceinline__ void pull_rows(const TableDev& T, const float* src, u
                                           int flag, int b0, int n_rows, float* __restrict__ out,
                                           int io_stride, int off, int lane) {
     constexpr int RP = 32 / LPR;
+    constexpr int U = LPR >= 8 ? 8 : LPR;  // rows in flight per lane group
     const int gl = lane % LPR;
     const int wstride = T.wstride, dim = T.dim;
-#pragma unroll 4
-    for (int p = 0; p < LPR; ++p) {
-        int r = p * RP + lane / LPR;
-        const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
-        unsigned long long idr = __shfl_sync(0xffffffffu, id, r);
-        int fl = __shfl_sync(0xffffffffu, flag, r);
-        int b = b0 + r;
-        if (b >= n_rows) continue;
-        float* dst = out + (size_t)b * io_stride + off;
-        if (T.vec4) {
-            for (int c = gl * 4; c < wstride; c += LPR * 4) {
-                float4 v;
-                if (fl == 1) v = ld_stream_v4(s + c);
-                else if (fl == 2) v = init_block_masked(T.init, idr, c, dim);
-                else v = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(dst + c) = v;
-            }
-        } else {
-            for (int c = gl; c < dim; c += LPR) {
-                float v = 0.f;
-                if (fl == 1) v = s[c];
-                else if (fl == 2) {
-                    float t[4];
-                    InitGen<float>::block4(T.init, idr, 0u, t);
-                    v = t[c & 3];
+    if (T.vec4) {
+        // warp-uniform trip count (the body shuffles): one iteration unless dim > 128
+        for (int cb = 0; cb < wstride; cb += LPR * 4) {
+            const int c0 = cb + gl * 4;
+            const bool cin = c0 < wstride;
+#pragma unroll 1
+            for (int p0 = 0; p0 < LPR; p0 += U) {
+                float4 v[U];
+                int fl[U];
+                unsigned long long idr[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int r = (p0 + u) * RP + lane / LPR;
+                    const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+                    idr[u] = __shfl_sync(0xffffffffu, id, r);
+                    fl[u] = __shfl_sync(0xffffffffu, flag, r);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (fl[u] == 1 && cin) v[u] = ld_stream_v4(s + c0);
                 }
-                dst[c] = v;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int b = b0 + (p0 + u) * RP + lane / LPR;
+                    if (b >= n_rows || !cin) continue;
+                    if (fl[u] == 2) v[u] = init_block_masked(&T.init, idr[u], c0, dim);
+                    *reinterpret_cast<float4*>(out + (size_t)b * io_stride + off + c0) = v[u];
+                }
+            }
+        }
+    } else {  // dim < 4: one lane per row
+        int b = b0 + lane;
+        if (b < n_rows) {
+            for (int c = 0; c < dim; ++c) {
+                float v = 0.f;
+                if (flag == 1) v = src[c];
+                else if (flag == 2) v = init_scalar(&T.init, id, c);
+                out[(size_t)b * io_stride + off + c] = v;
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long* __restrict__ ids,
                 float* __restrict__ out, int n_rows) {
+    extern __shared__ __align__(16) unsigned char exb_smem[];
+    const SmemView S = stage_plan(tables, P, exb_smem);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = P.W;
+    const int wic = threadIdx.x >> 5;
+    unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, false);
+    unsigned char* wbuf = stage_end + (size_t)wic * EXB_PULL_WARP_BUF;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(stage_end + 8 * (size_t)EXB_PULL_WARP_BUF) + wic;
+    unsigned parity = 0;
+    if (P.use_bulk) {
+        if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+        __syncwarp();
+    }
     for (int task = warp; task < P.num_tasks; task += nwarps) {
-        const int f = find_segment(P.task_prefix, P.F, task);
-        const int b0 = (task - P.task_prefix[f]) * 32;
+        const int f = find_segment(S.task_prefix, P.F, task);
+        const int b0 = (task - S.task_prefix[f]) * 32;
         if (b0 >= n_rows) continue;
-        const TableDev& T = tables[P.pt_table[P.feat_pt[f]]];
+        const TableDev& T = S.tab[S.feat_pt[f]];
         const int b = b0 + lane;
         unsigned long long id = 0;
         const float* src = nullptr;
         int flag = 0;
         if (b < n_rows) {
-            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + P.feat_col[f]);
+            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + S.feat_col[f]);
             if (!T.is_hash) {
                 if (id < T.vocab) {
                     int o = owner_of(T, id, W);
-                    unsigned long long row = local_row_of(T, id);
-                    src = T.w[o] + row * (unsigned long long)T.wstride;
+                    src = T.w[o] + local_row_of(T, id) * (unsigned long long)T.wstride;
                     flag = 1;
                 }
             } else if ((id >> 63) == 0) {
@@ -126,7 +231,11 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
                 }
             }
         }
-        const int off = P.feat_off[f];
+        const int off = S.feat_off[f];
+        if (P.use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
+            pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf, mbar, parity, P.status);
+            continue;
+        }
         switch (T.lpr) {
             case 1: pull_rows<1>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
             case 2: pull_rows<2>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
@@ -141,57 +250,78 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
 }
 
 // ------------------------------------------------------------ push + update
-#define EXB_MAX_SEG 1024  // max W*PT segments of the combine phase
+// Per-table counters live on their own 128-byte line (EXB_CTR_STRIDE words apart): every
+// table's appends would otherwise serialise in ONE L2 slice (measured: 19 us per warp task).
+#define EXB_CTR_STRIDE 32
 
-// find-or-insert `key` into plan-table pt's combine map; returns map position
-__device__ __forceinline__ unsigned cmap_insert(const PlanDev& P, int pt, unsigned long long key) {
-    const unsigned mask = P.pt_map_mask[pt];
-    unsigned long long* keys = P.cmap_keys + P.pt_map_off[pt];
+// Warp-collective find-or-insert of `key` (lanes with active == false only take part in
+// the vote) into plan-table pt's combine map; returns the map position. New keys are
+// appended to the table's unique list with ONE counter atomic per warp.
+__device__ __forceinline__ unsigned cmap_insert_warp(const PlanDev& P, const SmemView& S, int pt,
+                                                     unsigned long long key, bool active, int lane) {
+    const unsigned mask = S.map_mask[pt];
+    unsigned long long* keys = P.cmap_keys + S.map_off[pt];
     unsigned h = (unsigned)(exb_hash64(key) >> 20) & mask;
-    for (unsigned probe = 0; probe <= mask; ++probe) {
-        unsigned long long k = *(volatile unsigned long long*)&keys[h];
-        if (k == key) return h;
-        if (k == EXB_EMPTY_KEY) {
-            unsigned long long prev = atomicCAS(&keys[h], EXB_EMPTY_KEY, key);
-            if (prev == EXB_EMPTY_KEY) {
-                unsigned u = atomicAdd(&P.ucount[pt], 1u);
-                P.ulist[P.pt_ulist_off[pt] + u] = h;
-                return h;
-            }
-            if (prev == key) return h;
-        }
-        h = (h + 1) & mask;
+    bool won = false, done = !active;
+    for (unsigned probe = 0; probe <= mask && !done; ++probe) {
+        unsigned long long prev = atomicCAS(&keys[h], EXB_EMPTY_KEY, key);
+        if (prev == EXB_EMPTY_KEY) { won = true; done = true; }
+        else if (prev == key) done = true;
+        else h = (h + 1) & mask;
     }
-    set_error(P.status, EXB_ERR_CMAP_FULL);
-    return 0xFFFFFFFFu;
+    if (!done) { set_error(P.status, EXB_ERR_CMAP_FULL); h = 0xFFFFFFFFu; }
+    const unsigned wmask = __ballot_sync(0xffffffffu, won);
+    if (wmask) {
+        const int leader = __ffs(wmask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&P.ucount[pt * EXB_CTR_STRIDE], (unsigned)__popc(wmask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (won) P.ulist[S.ulist_off[pt] + base + (unsigned)__popc(wmask & ((1u << lane) - 1u))] = h;
+    }
+    return active ? h : 0xFFFFFFFFu;
 }
 
 // Move / accumulate the 32 rows of a warp task.
-// mode: 0 skip, 1 accumulate row into acc[h] (local red.add), 2 store row to dst (peer inbox)
+// mode: 0 skip, 1 accumulate row into dst (red.add), 2 store row to dst (peer inbox)
 template <int LPR>
 __device__ __forceinline__ void move_rows(const TableDev& T, const float* src, float* dst, int mode,
                                           int lane) {
     constexpr int RP = 32 / LPR;
+    constexpr int U = LPR >= 8 ? 8 : LPR;
     const int gl = lane % LPR;
     const int wstride = T.wstride, dim = T.dim;
-#pragma unroll 4
-    for (int p = 0; p < LPR; ++p) {
-        int r = p * RP + lane / LPR;
-        const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
-        float* d = (float*)__shfl_sync(0xffffffffu, (unsigned long long)dst, r);
-        int m = __shfl_sync(0xffffffffu, mode, r);
-        if (m == 0) continue;
-        if (T.vec4) {
-            for (int c = gl * 4; c < wstride; c += LPR * 4) {
-                float4 v = *reinterpret_cast<const float4*>(s + c);
-                if (m == 1) red_add_v4(d + c, v);
-                else *reinterpret_cast<float4*>(d + c) = v;
+    if (T.vec4) {
+        for (int cb = 0; cb < wstride; cb += LPR * 4) {  // warp-uniform trip count
+            const int c0 = cb + gl * 4;
+            const bool cin = c0 < wstride;
+#pragma unroll 1
+            for (int p0 = 0; p0 < LPR; p0 += U) {
+                float4 v[U];
+                float* d[U];
+                int m[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int r = (p0 + u) * RP + lane / LPR;
+                    const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+                    d[u] = (float*)__shfl_sync(0xffffffffu, (unsigned long long)dst, r);
+                    m[u] = __shfl_sync(0xffffffffu, mode, r);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!cin) m[u] = 0;
+                    if (m[u]) v[u] = ld_stream_v4(s + c0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (m[u] == 1) red_add_v4(d[u] + c0, v[u]);
+                    else if (m[u] == 2) *reinterpret_cast<float4*>(d[u] + c0) = v[u];
+                }
             }
-        } else {
-            for (int c = gl; c < dim; c += LPR) {
-                float v = s[c];
-                if (m == 1) red_add_f32(d + c, v);
-                else d[c] = v;
+        }
+    } else {
+        if (mode) {
+            for (int c = 0; c < dim; ++c) {
+                float v = src[c];
+                if (mode == 1) red_add_f32(dst + c, v);
+                else dst[c] = v;
             }
         }
     }
@@ -210,15 +340,16 @@ __device__ __forceinline__ void move_rows_dispatch(const TableDev& T, const floa
 }
 
 // block-wide exclusive prefix of ceil(cnt/32) over n (<= EXB_MAX_SEG) segments -> s_prefix[0..n]
-__device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, int* s_prefix) {
-    // each of the first 32 threads scans a contiguous chunk, then a warp scan of chunk sums
+__device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, int* s_prefix,
+                                                  int stride = 1) {
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         const int chunk = (n + 31) / 32;
         int beg = lane * chunk, end = min(n, beg + chunk);
         int sum = 0;
-        for (int i = beg; i < end; ++i) sum += (int)((cnt[i] + 31u) >> 5);
+        for (int i = beg; i < end; ++i)
+            sum += (int)((*(volatile const unsigned*)&cnt[(size_t)i * stride] + 31u) >> 5);
         int incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -227,7 +358,7 @@ __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, in
         int run = incl - sum;
         for (int i = beg; i < end; ++i) {
             s_prefix[i] = run;
-            run += (int)((cnt[i] + 31u) >> 5);
+            run += (int)((*(volatile const unsigned*)&cnt[(size_t)i * stride] + 31u) >> 5);
         }
         if (lane == 31) s_prefix[n] = incl;
     }
@@ -235,116 +366,184 @@ __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, in
 }
 
 template <int LPR>
-__device__ __forceinline__ void apply_rows(const TableDev& T, const PlanDev& P, int pt,
+__device__ __forceinline__ void apply_rows(const TableDev& T, const PlanDev& P, float* accbase,
                                            unsigned long long key, unsigned long long row, unsigned h,
                                            unsigned cnt, int flag /*0 skip,1 existing,2 new*/,
                                            int lane) {
     constexpr int RP = 32 / LPR;
+    constexpr int U = LPR >= 2 ? 2 : LPR;
     const int gl = lane % LPR;
     const int wstride = T.wstride, dim = T.dim, nslots = T.nslots, nsc = T.nscalars;
-    float* accbase = P.acc + P.pt_acc_off[pt];
     float* wloc = T.w[P.rank];
-#pragma unroll 2
-    for (int p = 0; p < LPR; ++p) {
-        int r = p * RP + lane / LPR;
-        unsigned long long keyr = __shfl_sync(0xffffffffu, key, r);
-        unsigned long long rowr = __shfl_sync(0xffffffffu, row, r);
-        unsigned hr = __shfl_sync(0xffffffffu, h, r);
-        unsigned cr = __shfl_sync(0xffffffffu, cnt, r);
-        int fl = __shfl_sync(0xffffffffu, flag, r);
-        if (fl == 0) continue;
-        float* wrow = wloc + rowr * (unsigned long long)wstride;
-        float* srow = T.state + rowr * (unsigned long long)T.sstride;
-        float* arow = accbase + (unsigned long long)hr * wstride;
-        // per-row scalar prologue (evaluated redundantly by the group, committed by lane 0)
-        float sc[2] = {0.f, 0.f}, nsc_v[2];
-        float* scal = srow + (size_t)nslots * wstride;
-        for (int i = 0; i < nsc; ++i) sc[i] = (fl == 2) ? opt_scalar_init<float>(T.opt, i) : scal[i];
-        RowCtx<float> rc = opt_row_prologue_pure<float>(T.opt, sc, (uint64_t)cr, nsc_v);
-        if (T.vec4) {
-            for (int c = gl * 4; c < wstride; c += LPR * 4) {
-                float4 g4 = *reinterpret_cast<float4*>(arow + c);
-                *reinterpret_cast<float4*>(arow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 w4, a4, b4;
-                float s0i = opt_slot_init<float>(T.opt, 0), s1i = opt_slot_init<float>(T.opt, 1);
-                if (fl == 2) {
-                    w4 = init_block_masked(T.init, keyr, c, dim);
-                    a4 = make_float4(s0i, s0i, s0i, s0i);
-                    b4 = make_float4(s1i, s1i, s1i, s1i);
-                } else {
-                    w4 = *reinterpret_cast<float4*>(wrow + c);
-                    a4 = nslots > 0 ? *reinterpret_cast<float4*>(srow + c) : make_float4(0, 0, 0, 0);
-                    b4 = nslots > 1 ? *reinterpret_cast<float4*>(srow + wstride + c)
-                                    : make_float4(0, 0, 0, 0);
-                }
-                float* w = &w4.x; float* a = &a4.x; float* b = &b4.x; const float* g = &g4.x;
+    const OptParams opt = T.opt;
+    const float s0i = opt_slot_init<float>(opt, 0), s1i = opt_slot_init<float>(opt, 1);
+    if (T.vec4) {
+#pragma unroll 1
+        for (int p0 = 0; p0 < LPR; p0 += U) {
+            float4 g4[U], w4[U], a4[U], b4[U];
+            float scv[U][2];
+            int fl[U];
+            unsigned long long rowr[U], keyr[U];
+            unsigned hr[U], cr[U];
+            // ---- issue every load of the batch
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (c + i < dim) opt_elem<float>(T.opt, rc, w[i], a[i], b[i], g[i]);
-                *reinterpret_cast<float4*>(wrow + c) = w4;
-                if (nslots > 0) *reinterpret_cast<float4*>(srow + c) = a4;
-                if (nslots > 1) *reinterpret_cast<float4*>(srow + wstride + c) = b4;
-            }
-        } else {
-            for (int c = gl; c < dim; c += LPR) {
-                float g = arow[c];
-                arow[c] = 0.f;
-                float w, a = 0.f, b = 0.f;
-                if (fl == 2) {
-                    float t[4];
-                    InitGen<float>::block4(T.init, keyr, 0u, t);
-                    w = t[c & 3];
-                    a = opt_slot_init<float>(T.opt, 0);
-                    b = opt_slot_init<float>(T.opt, 1);
-                } else {
-                    w = wrow[c];
-                    if (nslots > 0) a = srow[c];
-                    if (nslots > 1) b = srow[wstride + c];
+            for (int u = 0; u < U; ++u) {
+                int r = (p0 + u) * RP + lane / LPR;
+                keyr[u] = __shfl_sync(0xffffffffu, key, r);
+                rowr[u] = __shfl_sync(0xffffffffu, row, r);
+                hr[u] = __shfl_sync(0xffffffffu, h, r);
+                cr[u] = __shfl_sync(0xffffffffu, cnt, r);
+                fl[u] = __shfl_sync(0xffffffffu, flag, r);
+                const int c = gl * 4;
+                g4[u] = w4[u] = a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                scv[u][0] = scv[u][1] = 0.f;
+                if (fl[u] && c < wstride) {
+                    float* arow = accbase + (unsigned long long)hr[u] * wstride;
+                    g4[u] = *reinterpret_cast<float4*>(arow + c);
+                    if (fl[u] == 1) {
+                        const float* wrow = wloc + rowr[u] * (unsigned long long)wstride;
+                        const float* srow = T.state + rowr[u] * (unsigned long long)T.sstride;
+                        w4[u] = *reinterpret_cast<const float4*>(wrow + c);
+                        if (nslots > 0) a4[u] = *reinterpret_cast<const float4*>(srow + c);
+                        if (nslots > 1) b4[u] = *reinterpret_cast<const float4*>(srow + wstride + c);
+                        for (int i = 0; i < nsc; ++i) scv[u][i] = srow[(size_t)nslots * wstride + i];
+                    }
                 }
-                opt_elem<float>(T.opt, rc, w, a, b, g);
-                wrow[c] = w;
-                if (nslots > 0) srow[c] = a;
-                if (nslots > 1) srow[wstride + c] = b;
+            }
+            // ---- compute + write back
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!fl[u]) continue;
+                float* wrow = wloc + rowr[u] * (unsigned long long)wstride;
+                float* srow = T.state + rowr[u] * (unsigned long long)T.sstride;
+                float* arow = accbase + (unsigned long long)hr[u] * wstride;
+                float sc[2] = {scv[u][0], scv[u][1]}, nsc_v[2];
+                if (fl[u] == 2)
+                    for (int i = 0; i < nsc; ++i) sc[i] = opt_scalar_init<float>(opt, i);
+                RowCtx<float> rc = opt_row_prologue_pure<float>(opt, sc, (uint64_t)cr[u], nsc_v);
+                for (int c = gl * 4; c < wstride; c += LPR * 4) {
+                    float4 g, w, a, b;
+                    if (c == gl * 4) { g = g4[u]; w = w4[u]; a = a4[u]; b = b4[u]; }
+                    else {  // dim > 128: remaining chunks, simple path
+                        g = *reinterpret_cast<float4*>(arow + c);
+                        w = a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (fl[u] == 1) {
+                            w = *reinterpret_cast<float4*>(wrow + c);
+                            if (nslots > 0) a = *reinterpret_cast<float4*>(srow + c);
+                            if (nslots > 1) b = *reinterpret_cast<float4*>(srow + wstride + c);
+                        }
+                    }
+                    if (fl[u] == 2) {
+                        w = init_block_masked(&T.init, keyr[u], c, dim);
+                        a = make_float4(s0i, s0i, s0i, s0i);
+                        b = make_float4(s1i, s1i, s1i, s1i);
+                    }
+                    *reinterpret_cast<float4*>(arow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c + 0 < dim) opt_elem<float>(opt, rc, w.x, a.x, b.x, g.x);
+                    if (c + 1 < dim) opt_elem<float>(opt, rc, w.y, a.y, b.y, g.y);
+                    if (c + 2 < dim) opt_elem<float>(opt, rc, w.z, a.z, b.z, g.z);
+                    if (c + 3 < dim) opt_elem<float>(opt, rc, w.w, a.w, b.w, g.w);
+                    *reinterpret_cast<float4*>(wrow + c) = w;
+                    if (nslots > 0) *reinterpret_cast<float4*>(srow + c) = a;
+                    if (nslots > 1) *reinterpret_cast<float4*>(srow + wstride + c) = b;
+                }
+                if (gl == 0)
+                    for (int i = 0; i < nsc; ++i) srow[(size_t)nslots * wstride + i] = nsc_v[i];
             }
         }
-        if (gl == 0)
-            for (int i = 0; i < nsc; ++i) scal[i] = nsc_v[i];
+    } else if (flag) {  // dim < 4: one lane per row
+        float* wrow = wloc + row * (unsigned long long)wstride;
+        float* srow = T.state + row * (unsigned long long)T.sstride;
+        float* arow = accbase + (unsigned long long)h * wstride;
+        float sc[2] = {0.f, 0.f}, nsc_v[2];
+        for (int i = 0; i < nsc; ++i)
+            sc[i] = (flag == 2) ? opt_scalar_init<float>(opt, i) : srow[(size_t)nslots * wstride + i];
+        RowCtx<float> rc = opt_row_prologue_pure<float>(opt, sc, (uint64_t)cnt, nsc_v);
+        for (int c = 0; c < dim; ++c) {
+            float g = arow[c];
+            arow[c] = 0.f;
+            float w, a = s0i, b = s1i;
+            if (flag == 2) {
+                w = init_scalar(&T.init, key, c);
+            } else {
+                w = wrow[c];
+                if (nslots > 0) a = srow[c];
+                if (nslots > 1) b = srow[wstride + c];
+            }
+            opt_elem<float>(opt, rc, w, a, b, g);
+            wrow[c] = w;
+            if (nslots > 0) srow[c] = a;
+            if (nslots > 1) srow[wstride + c] = b;
+        }
+        for (int i = 0; i < nsc; ++i) srow[(size_t)nslots * wstride + i] = nsc_v[i];
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                        const long long* __restrict__ ids, const float* __restrict__ grads,
                        int n_rows) {
-    __shared__ int s_prefix[EXB_MAX_SEG + 1];
+    extern __shared__ __align__(16) unsigned char exb_smem[];
+    const SmemView S = stage_plan(tables, P, exb_smem);
+    int* s_prefix = S.seg_prefix;
+    const int wic = threadIdx.x >> 5;
+    unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, true);
+    unsigned char* wbuf = stage_end + (size_t)wic * EXB_APPLY_WARP_BUF;
+    WarpMeta* wmeta = reinterpret_cast<WarpMeta*>(stage_end + 8 * (size_t)EXB_APPLY_WARP_BUF) + wic;
+    unsigned long long* mbar =
+        reinterpret_cast<unsigned long long*>(stage_end + 8 * (size_t)EXB_APPLY_WARP_BUF + 8 * sizeof(WarpMeta)) + wic;
+    unsigned parity = 0;
+    if (P.use_bulk) {
+        if ((threadIdx.x & 31) == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+        __syncwarp();
+    }
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = P.W, PT = P.PT, rank = P.rank;
+    // phase clock: CTA 0 / thread 0 stamps %globaltimer at every phase boundary into
+    // stats[8..15] (read by utils.timers; the in-kernel equivalent of the reference's VTIMER)
+#define EXB_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[8 + (i)] = globaltimer_ns(); } while (0)
+    EXB_STAMP(0);
+#ifdef EXB_PROBE
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[21] = globaltimer_ns();
+#endif
 
     // ---------------- P1: dispatch (remote ids -> owner inbox, local ids -> combine map)
     for (int task = warp; task < P.num_tasks; task += nwarps) {
-        const int f = find_segment(P.task_prefix, P.F, task);
-        const int b0 = (task - P.task_prefix[f]) * 32;
+        const int f = find_segment(S.task_prefix, P.F, task);
+        const int b0 = (task - S.task_prefix[f]) * 32;
         if (b0 >= n_rows) continue;
-        const int pt = P.feat_pt[f];
-        const TableDev& T = tables[P.pt_table[pt]];
+        const int pt = S.feat_pt[f];
+        const TableDev& T = S.tab[pt];
         const int b = b0 + lane;
         unsigned long long id = 0;
         int owner = -1;
         if (b < n_rows) {
-            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + P.feat_col[f]);
+            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + S.feat_col[f]);
             bool ok = T.is_hash ? ((id >> 63) == 0) : (id < T.vocab);
             if (ok) owner = owner_of(T, id, W);
         }
-        const float* src = grads + (size_t)b * P.io_stride + P.feat_off[f];
+        const float* src = grads + (size_t)b * P.io_stride + S.feat_off[f];
         float* dst = nullptr;
         int mode = 0;
-        if (owner == rank) {
-            unsigned h = cmap_insert(P, pt, id);
+#ifdef EXB_PROBE
+        const bool probe = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
+        if (probe) { P.stats[16] = globaltimer_ns(); P.stats[17] = id; }
+#endif
+        {
+            unsigned h = cmap_insert_warp(P, S, pt, id, owner == rank, lane);
+#ifdef EXB_PROBE
+            if (probe) { P.stats[18] = globaltimer_ns() + (h & 0); }
+#endif
             if (h != 0xFFFFFFFFu) {
-                atomicAdd(&P.cmap_cnt[P.pt_map_off[pt] + h], 1u);
-                dst = P.acc + P.pt_acc_off[pt] + (unsigned long long)h * T.wstride;
+                unsigned old = atomicAdd(&P.cmap_cnt[S.map_off[pt] + h], 1u);
+#ifdef EXB_PROBE
+                if (probe) { P.stats[19] = globaltimer_ns() + (old & 0); }
+#else
+                (void)old;
+#endif
+                dst = P.acc + S.acc_off[pt] + (unsigned long long)h * T.wstride;
                 mode = 1;
             }
         }
@@ -353,13 +552,14 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             if (owner >= 0 && owner != rank) {
                 int leader = __ffs(m) - 1;
                 unsigned base = 0;
-                if (lane == leader) base = atomicAdd(&P.send_cnt[owner * PT + pt], (unsigned)__popc(m));
+                if (lane == leader)
+                    base = atomicAdd(&P.send_cnt[(owner * PT + pt) * EXB_CTR_STRIDE], (unsigned)__popc(m));
                 base = __shfl_sync(m, base, leader);
                 unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-                if (pos < P.pt_cap[pt]) {
-                    P.inbox_keys[owner][(unsigned long long)rank * P.src_key_stride + P.pt_key_off[pt] + pos] = id;
+                if (pos < S.cap[pt]) {
+                    P.inbox_keys[owner][(unsigned long long)rank * P.src_key_stride + S.key_off[pt] + pos] = id;
                     dst = P.inbox_grads[owner] + (unsigned long long)rank * P.src_grad_stride +
-                          P.pt_grad_off[pt] + (unsigned long long)pos * T.wstride;
+                          S.grad_off[pt] + (unsigned long long)pos * T.wstride;
                     mode = 2;
                 } else {
                     set_error(P.status, EXB_ERR_INBOX_OVERFLOW);
@@ -367,20 +567,25 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             }
         }
         move_rows_dispatch(T, src, dst, mode, lane);
+#ifdef EXB_PROBE
+        if (probe) { __threadfence(); P.stats[20] = globaltimer_ns(); }
+#endif
     }
 
+    EXB_STAMP(1);
     if (W > 1) {
         // ---------------- B1: publish counts, cross-GPU barrier
         grid_barrier(P, true, [&]() {
             for (int i = threadIdx.x; i < W * PT; i += blockDim.x) {
                 int o = i / PT, pt = i - o * PT;
-                unsigned c = P.send_cnt[i];
-                if (c > P.pt_cap[pt]) c = P.pt_cap[pt];
+                unsigned c = *(volatile unsigned*)&P.send_cnt[i * EXB_CTR_STRIDE];
+                if (c > S.cap[pt]) c = S.cap[pt];
                 if (o != rank) P.inbox_cnt[o][rank * PT + pt] = c;
-                P.send_cnt[i] = 0;
+                P.send_cnt[i * EXB_CTR_STRIDE] = 0;
             }
             peer_barrier(P);
         });
+        EXB_STAMP(2);
         // ---------------- P3: combine inbox entries of every remote source
         const unsigned* mycnt = P.inbox_cnt[rank];
         block_task_prefix(mycnt, W * PT, s_prefix);
@@ -389,21 +594,22 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             const int seg = find_segment(s_prefix, W * PT, task);
             const int s = seg / PT, pt = seg - s * PT;
             if (s == rank) continue;  // local ids never travel through the inbox
-            const TableDev& T = tables[P.pt_table[pt]];
+            const TableDev& T = S.tab[pt];
             const unsigned e = (unsigned)(task - s_prefix[seg]) * 32u + lane;
-            const unsigned n = mycnt[seg];
+            const unsigned n = *(volatile const unsigned*)&mycnt[seg];
             const float* src = nullptr;
             float* dst = nullptr;
             int mode = 0;
-            if (e < n) {
-                unsigned long long key =
-                    P.inbox_keys[rank][(unsigned long long)s * P.src_key_stride + P.pt_key_off[pt] + e];
-                unsigned h = cmap_insert(P, pt, key);
+            {
+                unsigned long long key = 0;
+                if (e < n)
+                    key = P.inbox_keys[rank][(unsigned long long)s * P.src_key_stride + S.key_off[pt] + e];
+                unsigned h = cmap_insert_warp(P, S, pt, key, e < n, lane);
                 if (h != 0xFFFFFFFFu) {
-                    atomicAdd(&P.cmap_cnt[P.pt_map_off[pt] + h], 1u);
+                    atomicAdd(&P.cmap_cnt[S.map_off[pt] + h], 1u);
                     src = P.inbox_grads[rank] + (unsigned long long)s * P.src_grad_stride +
-                          P.pt_grad_off[pt] + (unsigned long long)e * T.wstride;
-                    dst = P.acc + P.pt_acc_off[pt] + (unsigned long long)h * T.wstride;
+                          S.grad_off[pt] + (unsigned long long)e * T.wstride;
+                    dst = P.acc + S.acc_off[pt] + (unsigned long long)h * T.wstride;
                     mode = 1;
                 }
             }
@@ -412,23 +618,29 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     }
 
     // ---------------- B2: all accumulations visible
+    EXB_STAMP(3);
     grid_barrier(P, false, [&]() {});
+    EXB_STAMP(4);
 
     // ---------------- P5: apply optimizer to every unique row
-    block_task_prefix(P.ucount, PT, s_prefix);
+    block_task_prefix(P.ucount, PT, s_prefix, EXB_CTR_STRIDE);
     const int ntask5 = s_prefix[PT];
-    unsigned long long n_unique_local = 0;
+    unsigned n_unique_local = 0;
     for (int task = warp; task < ntask5; task += nwarps) {
         const int pt = find_segment(s_prefix, PT, task);
-        const TableDev& T = tables[P.pt_table[pt]];
+        const TableDev& T = S.tab[pt];
         const unsigned u = (unsigned)(task - s_prefix[pt]) * 32u + lane;
-        const unsigned n = P.ucount[pt];
+        const unsigned n = *(volatile unsigned*)&P.ucount[pt * EXB_CTR_STRIDE];
+#ifdef EXB_PROBE
+        const bool probe5 = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
+        if (probe5) P.stats[22] = globaltimer_ns();
+#endif
         unsigned long long key = 0, row = 0;
         unsigned h = 0, cnt = 0;
         int flag = 0;
         if (u < n) {
-            h = P.ulist[P.pt_ulist_off[pt] + u];
-            const unsigned long long mo = P.pt_map_off[pt] + h;
+            h = P.ulist[S.ulist_off[pt] + u];
+            const unsigned long long mo = S.map_off[pt] + h;
             key = *(volatile unsigned long long*)&P.cmap_keys[mo];
             cnt = *(volatile unsigned*)&P.cmap_cnt[mo];
             P.cmap_keys[mo] = EXB_EMPTY_KEY;
@@ -445,7 +657,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                     if (k == key) { flag = 1; break; }
                     if (k == EXB_EMPTY_KEY) {
                         unsigned long long prev = atomicCAS(&keys[hh], EXB_EMPTY_KEY, key);
-                        if (prev == EXB_EMPTY_KEY) { flag = 2; atomicAdd(T.size_ctr, 1ull); break; }
+                        if (prev == EXB_EMPTY_KEY) { flag = 2; break; }
                         if (prev == key) { flag = 1; break; }
                     }
                     hh = (hh + 1) & mask;
@@ -455,23 +667,42 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             }
             if (flag) ++n_unique_local;
         }
-        switch (T.lpr) {
-            case 1: apply_rows<1>(T, P, pt, key, row, h, cnt, flag, lane); break;
-            case 2: apply_rows<2>(T, P, pt, key, row, h, cnt, flag, lane); break;
-            case 4: apply_rows<4>(T, P, pt, key, row, h, cnt, flag, lane); break;
-            case 8: apply_rows<8>(T, P, pt, key, row, h, cnt, flag, lane); break;
-            case 16: apply_rows<16>(T, P, pt, key, row, h, cnt, flag, lane); break;
-            default: apply_rows<32>(T, P, pt, key, row, h, cnt, flag, lane); break;
+        if (T.is_hash) {   // one size-counter atomic per warp
+            const unsigned nm = __ballot_sync(0xffffffffu, flag == 2);
+            if (nm && lane == __ffs(nm) - 1) atomicAdd(T.size_ctr, (unsigned long long)__popc(nm));
         }
+        float* accbase = P.acc + S.acc_off[pt];
+#ifdef EXB_PROBE
+        if (probe5) P.stats[23] = globaltimer_ns() + (row & 0) + (cnt & 0);
+#endif
+        if (P.use_bulk && T.vec4 && (2 * T.wstride + T.sstride) * 4 <= EXB_APPLY_WARP_BUF) {
+            apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, mbar, parity);
+            continue;
+        }
+        switch (T.lpr) {
+            case 1: apply_rows<1>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+            case 2: apply_rows<2>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+            case 4: apply_rows<4>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+            case 8: apply_rows<8>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+            case 16: apply_rows<16>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+            default: apply_rows<32>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        }
+#ifdef EXB_PROBE
+        if (probe5) { __threadfence(); P.stats[24] = globaltimer_ns(); }
+#endif
     }
-    if (n_unique_local) atomicAdd(&P.stats[2], n_unique_local);
+    n_unique_local = __reduce_add_sync(0xffffffffu, n_unique_local);
+    if (lane == 0 && n_unique_local) atomicAdd(&P.stats[2], (unsigned long long)n_unique_local);
+    EXB_STAMP(5);
 
     // ---------------- B3: reset per-step counters; cross-GPU "update done"
     grid_barrier(P, W > 1, [&]() {
-        for (int i = threadIdx.x; i < PT; i += blockDim.x) P.ucount[i] = 0;
+        for (int i = threadIdx.x; i < PT; i += blockDim.x) P.ucount[i * EXB_CTR_STRIDE] = 0;
         if (threadIdx.x == 0) atomicAdd(&P.stats[1], (unsigned long long)n_rows * P.F);
         if (W > 1) peer_barrier(P);
     });
+    EXB_STAMP(6);
+#undef EXB_STAMP
 }
 
 }  // namespace exb

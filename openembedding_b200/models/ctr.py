@@ -57,7 +57,7 @@ class FusedEmbeddings(nn.Module):
     column (`col`), e.g. the dim-D and the dim-1 table of one sparse feature.
     """
 
-    def __init__(self, specs, batch, optimizer, num_shards=None):
+    def __init__(self, specs, batch, optimizer, num_shards=None, ncols=None):
         super().__init__()
         ctx = get_context()
         self.ctx = ctx
@@ -70,7 +70,7 @@ class FusedEmbeddings(nn.Module):
             ctx.set_initializer(m, s.get("initializer", {"category": "constant", "value": 0.0}))
             ctx.set_optimizer(m, optimizer)
             self.metas.append(m)
-        self.group = ctx.backend.make_group(self.metas, batch, feat_cols=[s["col"] for s in specs])
+        self.group = ctx.backend.make_group(self.metas, batch, feat_cols=[s["col"] for s in specs], ncols=ncols)
         self.slices = self.group.feature_slices()
         self.io_stride = self.group.io_stride
         self.anchor = nn.Parameter(torch.zeros(1, device=ctx.device))  # keeps autograd attached
@@ -154,7 +154,7 @@ class CTRModel(nn.Module):
             specs += [{"vocab": vocab_sizes[f], "dim": embedding_dim, "col": f, "initializer": zero}
                       for f in self.server]
         specs += [{"vocab": vocab_sizes[f], "dim": 1, "col": f, "initializer": zero} for f in self.server]
-        self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards) if specs else None
+        self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards, ncols=nf) if specs else None
         ns = len(self.server)
         if self.sparse is not None:
             sl = self.sparse.slices

@@ -167,16 +167,27 @@ class CudaEngine:
                 plan.connected = True
 
     # ---------------------------------------------------------------- plans
-    def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None):
-        return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols)
+    def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None):
+        return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols, ncols)
 
     # --------------------------------------------------------------- status
     def status(self):
         st = ctypes.c_int32(0)
-        stats = _u64arr(3)
+        stats = _u64arr(32)
         _native.cuda_check(self.lib.exb_engine_status(self.h, ctypes.byref(st), stats), "status")
+        t = [int(stats[8 + i]) for i in range(7)]
+        names = ["dispatch", "barrier_publish", "combine", "barrier_acc", "apply", "barrier_done"]
+        phases = {}
+        if t[0] and t[6] >= t[0]:
+            prev = t[0]
+            for i, nm in enumerate(names):
+                cur = t[i + 1] if t[i + 1] else prev     # phases skipped at world==1 keep the clock
+                phases[nm] = (cur - prev) / 1e3
+                prev = cur
+            phases["total"] = (t[6] - t[0]) / 1e3
         return int(st.value), {"pull_indices": int(stats[0]), "push_indices": int(stats[1]),
-                               "update_unique": int(stats[2])}
+                               "update_unique": int(stats[2]), "last_push_update_us": phases,
+                               "probe": [int(stats[i]) for i in range(16, 28)]}
 
     def check(self):
         code, _ = self.status()
@@ -238,7 +249,7 @@ class CudaEngine:
 class SparsePlan:
     """Fused lookup/update over F features of one batch (ids ``[B, F]`` int64)."""
 
-    def __init__(self, engine, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None):
+    def __init__(self, engine, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None):
         self.e = engine
         self.lib = engine.lib
         self.F = len(feat_tables)
@@ -258,7 +269,7 @@ class SparsePlan:
         self.feat_offsets = [int(o) for o in feat_offsets]
         self.io_stride = int(io_stride) if io_stride is not None else total
         self.feat_cols = [int(c) for c in (feat_cols if feat_cols is not None else range(self.F))]
-        self.ncols = max(self.feat_cols) + 1
+        self.ncols = int(ncols) if ncols else max(self.feat_cols) + 1
         ft = (ctypes.c_int32 * self.F)(*self.feat_tables)
         fo = (ctypes.c_int32 * self.F)(*self.feat_offsets)
         fc = (ctypes.c_int32 * self.F)(*self.feat_cols)
