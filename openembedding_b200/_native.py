@@ -110,6 +110,8 @@ def cuda():
         P(lib, "exb_table_scatter", c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64])
         P(lib, "exb_table_clear", c_int, [c_void_p, c_int])
         P(lib, "exb_table_rehash", c_int, [c_void_p, c_int, c_uint64])
+        P(lib, "exb_raw_alloc", c_uint64, [c_int, c_uint64])
+        P(lib, "exb_raw_free", c_int, [c_uint64])
         P(lib, "exb_ipc_get_handle", c_int, [c_uint64, c_char_p])
         P(lib, "exb_ipc_open_handle", c_uint64, [c_char_p])
         P(lib, "exb_ipc_close_handle", c_int, [c_uint64])

@@ -1,21 +1,23 @@
-// bulk_rows.cuh -- row movement with the Blackwell bulk-copy engine (1-D TMA).
+// bulk_rows.cuh -- asynchronous row movement through shared memory.
 //
-// Measured on B200 (profiles/sparse_v0.md): a random 256-byte row in a 16-54 GB table
+// Measured on B200 (profiles/sparse_path.md): a random 256-byte row in a 16-54 GB table
 // costs 2.5-5 us to fetch (DRAM + TLB miss), so a register-staged gather is purely
-// latency-bound: 8 rows in flight per lane group, 25 % occupancy, 8 % of DRAM bandwidth.
-// Here every lane owns one ROW and hands it to the copy engine:
-//     cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes   (SASS: UBLKCP)
-// No registers are held while the bytes are in flight, a warp keeps 32 rows (8-24 KB) in
-// flight and an SM several hundred. Rows leave shared memory the same way
-// (cp.async.bulk.global.shared::cta). Works on any global address, i.e. also on
-// peer-mapped (NVLink) table slabs.
+// latency-bound (8 rows in flight per lane group, 25 % occupancy, 8 % of DRAM bandwidth).
+// Two async mechanisms were tried:
+//   * 1-D TMA, one cp.async.bulk (UBLKCP) per row: correct, but the per-SM TMA unit
+//     retires one small copy every ~50-60 cycles -> ~12 us per 384-copy pass; kept only as
+//     helpers (bulk_g2s / bulk_s2g) for large contiguous moves;
+//   * cp.async 16-byte (LDGSTS): a warp instruction moves 512 B in ~8 issue cycles, holds
+//     no registers while in flight and queues arbitrarily deep -> the path used below.
+// A warp keeps a whole pass (32 weight rows, or 16 x {weights, state, accumulator}) in
+// flight; peer-mapped (NVLink) addresses take the same path.
 #pragma once
 #include "exb_common.cuh"
 
 namespace exb {
 
 #define EXB_PULL_WARP_BUF 8192    // bytes of row staging per warp in the pull kernel
-#define EXB_APPLY_WARP_BUF 12288  // bytes per warp in the apply phase (w | state | acc rows)
+#define EXB_APPLY_WARP_BUF 10240  // bytes per warp in the apply phase (w | state | acc rows)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -62,52 +64,55 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 __device__ __noinline__ float4 init_block_masked(const InitParams* I, unsigned long long id, int c, int dim);
 
-// Pull the 32 rows of a warp task through shared memory.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Pull the 32 rows of a warp task through shared memory (cp.async gather, coalesced write-out).
 // Lane l holds (src, id, flag) of row l. buf: EXB_PULL_WARP_BUF bytes owned by this warp.
 __device__ __forceinline__ void pull_rows_bulk(const TableDev& T, const float* src, unsigned long long id,
                                                int flag, int b0, int n_rows, float* __restrict__ out,
                                                int io_stride, int off, int lane, unsigned char* buf,
                                                unsigned long long* mbar, unsigned& parity, int* status) {
-    const unsigned rowbytes = (unsigned)T.wstride * 4u;
+    (void)mbar; (void)parity; (void)status;
+    const int wstride = T.wstride;
+    const unsigned rowbytes = (unsigned)wstride * 4u;
     const int R = min(32, (int)(EXB_PULL_WARP_BUF / rowbytes));   // rows per pass (warp uniform)
+    const int lpr = T.lpr, gl = lane % lpr, RP = 32 / lpr;
+    float* rows = reinterpret_cast<float*>(buf);
     for (int r0 = 0; r0 < 32; r0 += R) {
-        const int r = r0 + lane;
-        const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r & 31);
-        const unsigned long long idr = __shfl_sync(0xffffffffu, id, r & 31);
-        int fl = __shfl_sync(0xffffffffu, flag, r & 31);
-        const int b = b0 + r;
-        const bool mine = lane < R && r < 32 && b < n_rows;
-        if (!mine) fl = -1;
-        float* row = reinterpret_cast<float*>(buf + (size_t)lane * rowbytes);
-        const unsigned total = __reduce_add_sync(0xffffffffu, fl == 1 ? rowbytes : 0u);
-        if (total) {
-            if (lane == 0) mbar_expect_tx(mbar, total);
-            __syncwarp();
-            if (fl == 1) bulk_g2s(row, s, rowbytes, mbar);
+        // ---- issue: lane group g copies rows g, g+RP, ... of this pass, 16 bytes per lane
+        for (int jb = 0; jb < R; jb += RP) {             // warp-uniform trip count (body shuffles)
+            const int j = jb + lane / lpr, r = r0 + j;
+            const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r & 31);
+            const int fl = __shfl_sync(0xffffffffu, flag, r & 31);
+            if (j < R && r < 32 && fl == 1)
+                for (int c = gl * 4; c < wstride; c += lpr * 4) cp_async16(rows + (size_t)j * wstride + c, s + c);
         }
-        if (fl == 0 || fl == 2) {   // invalid id -> zeros, missing hash row -> initializer value
-            for (int c = 0; c < T.wstride; c += 4) {
+        cp_async_commit_wait();
+        __syncwarp();
+        // ---- write out (request order), zeros / initializer values for rows that were not loaded
+        for (int jb = 0; jb < R; jb += RP) {
+            const int j = jb + lane / lpr, r = r0 + j;
+            const unsigned long long idr = __shfl_sync(0xffffffffu, id, r & 31);
+            const int fl = __shfl_sync(0xffffffffu, flag, r & 31);
+            const int b = b0 + r;
+            if (j >= R || r >= 32 || b >= n_rows) continue;
+            float* dst = out + (size_t)b * io_stride + off;
+            for (int c = gl * 4; c < wstride; c += lpr * 4) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (fl == 2) v = init_block_masked(&T.init, idr, c, T.dim);
-                *reinterpret_cast<float4*>(row + c) = v;
+                if (fl == 1) v = *reinterpret_cast<const float4*>(rows + (size_t)j * wstride + c);
+                else if (fl == 2) v = init_block_masked(&T.init, idr, c, T.dim);
+                *reinterpret_cast<float4*>(dst + c) = v;
             }
         }
-        if (total) {
-            mbar_wait(mbar, parity, status);
-            parity ^= 1u;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (fl >= 0) bulk_s2g(out + (size_t)b * io_stride + off, row, rowbytes);
-        bulk_commit();
-        bulk_wait_read();
         __syncwarp();
     }
 }
-
-}  // namespace exb
-
-namespace exb {
 
 struct WarpMeta {   // per-warp row metadata of the apply phase (shared memory)
     unsigned long long key[32];
@@ -117,13 +122,15 @@ struct WarpMeta {   // per-warp row metadata of the apply phase (shared memory)
     int flag[32];
 };
 
-// Apply the optimizer to the (up to) 32 unique rows of a warp task; weights, state and
-// accumulator rows travel through shared memory with bulk copies.
+// Apply the optimizer to the (up to) 32 unique rows of a warp task: weights, state and
+// accumulator rows are gathered into shared memory with cp.async, the math reads them from
+// there and writes results straight back to global memory.
 // Lane l holds (key,row,h,cnt,flag) of row l on entry.
 __device__ __forceinline__ void apply_rows_bulk(const TableDev& T, const PlanDev& P, float* accbase,
                                                 unsigned long long key, unsigned long long row, unsigned h,
                                                 unsigned cnt, int flag, int lane, unsigned char* buf,
                                                 WarpMeta* M, unsigned long long* mbar, unsigned& parity) {
+    (void)mbar; (void)parity;
     const int wstride = T.wstride, sstride = T.sstride, dim = T.dim, nslots = T.nslots, nsc = T.nscalars;
     const unsigned wb = (unsigned)wstride * 4u, sb = (unsigned)sstride * 4u;
     const int R = min(32, (int)(EXB_APPLY_WARP_BUF / (2u * wb + sb)));
@@ -137,75 +144,64 @@ __device__ __forceinline__ void apply_rows_bulk(const TableDev& T, const PlanDev
     float* sbuf = reinterpret_cast<float*>(buf + (size_t)R * wb);
     float* abuf = reinterpret_cast<float*>(buf + (size_t)R * (wb + sb));
     for (int r0 = 0; r0 < 32; r0 += R) {
-        const int r = r0 + lane;
-        const bool mine = lane < R && r < 32;
-        const int fl = mine ? M->flag[r] : 0;
-        float* wrow_s = wbuf + (size_t)lane * wstride;
-        float* srow_s = sbuf + (size_t)lane * sstride;
-        float* arow_s = abuf + (size_t)lane * wstride;
-        unsigned long long grow = mine ? M->row[r] : 0ull;
-        unsigned gh = mine ? M->h[r] : 0u;
-        const unsigned bytes = fl == 1 ? (2u * wb + sb) : (fl == 2 ? wb : 0u);
-        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
-        if (total) {
-            if (lane == 0) mbar_expect_tx(mbar, total);
-            __syncwarp();
-            if (fl) bulk_g2s(arow_s, accbase + (unsigned long long)gh * wstride, wb, mbar);
-            if (fl == 1) {
-                bulk_g2s(wrow_s, wloc + grow * (unsigned long long)wstride, wb, mbar);
-                bulk_g2s(srow_s, T.state + grow * (unsigned long long)sstride, sb, mbar);
-            }
-            mbar_wait(mbar, parity, P.status);
-            parity ^= 1u;
-        }
-        __syncwarp();
-        // ---- math out of shared memory: lane group `lane / lpr` walks rows jj, jj+RP, ...
+        // ---- gather: lane group g fetches rows g, g+RP, ... of the pass
         for (int jj = lane / lpr; jj < R; jj += RP) {
             const int rr = r0 + jj;
             if (rr >= 32) break;
             const int f = M->flag[rr];
             if (!f) continue;
-            float* wr = wbuf + (size_t)jj * wstride;
-            float* sr = sbuf + (size_t)jj * sstride;
-            float* ar = abuf + (size_t)jj * wstride;
+            const float* ga = accbase + (unsigned long long)M->h[rr] * wstride;
+            for (int c = gl * 4; c < wstride; c += lpr * 4) cp_async16(abuf + (size_t)jj * wstride + c, ga + c);
+            if (f == 1) {
+                const float* gw = wloc + M->row[rr] * (unsigned long long)wstride;
+                const float* gs = T.state + M->row[rr] * (unsigned long long)sstride;
+                for (int c = gl * 4; c < wstride; c += lpr * 4) cp_async16(wbuf + (size_t)jj * wstride + c, gw + c);
+                for (int c = gl * 4; c < sstride; c += lpr * 4) cp_async16(sbuf + (size_t)jj * sstride + c, gs + c);
+            }
+        }
+        cp_async_commit_wait();
+        __syncwarp();
+        // ---- math out of shared memory, results go straight to global
+        for (int jj = lane / lpr; jj < R; jj += RP) {
+            const int rr = r0 + jj;
+            if (rr >= 32) break;
+            const int f = M->flag[rr];
+            if (!f) continue;
+            const float* wr = wbuf + (size_t)jj * wstride;
+            const float* sr = sbuf + (size_t)jj * sstride;
+            const float* ar = abuf + (size_t)jj * wstride;
+            float* gw = wloc + M->row[rr] * (unsigned long long)wstride;
+            float* gs = T.state + M->row[rr] * (unsigned long long)sstride;
+            float* ga = accbase + (unsigned long long)M->h[rr] * wstride;
             float sc[2] = {0.f, 0.f}, nsc_v[2];
             for (int i = 0; i < nsc; ++i)
                 sc[i] = (f == 2) ? opt_scalar_init<float>(opt, i) : sr[(size_t)nslots * wstride + i];
             RowCtx<float> rc = opt_row_prologue_pure<float>(opt, sc, (uint64_t)M->cnt[rr], nsc_v);
             for (int c = gl * 4; c < wstride; c += lpr * 4) {
-                float4 g = *reinterpret_cast<float4*>(ar + c);
+                float4 g = *reinterpret_cast<const float4*>(ar + c);
                 float4 w, a = make_float4(s0i, s0i, s0i, s0i), b = make_float4(s1i, s1i, s1i, s1i);
                 if (f == 2) {
                     w = init_block_masked(&T.init, M->key[rr], c, dim);
                 } else {
-                    w = *reinterpret_cast<float4*>(wr + c);
-                    if (nslots > 0) a = *reinterpret_cast<float4*>(sr + c);
-                    if (nslots > 1) b = *reinterpret_cast<float4*>(sr + wstride + c);
+                    w = *reinterpret_cast<const float4*>(wr + c);
+                    if (nslots > 0) a = *reinterpret_cast<const float4*>(sr + c);
+                    if (nslots > 1) b = *reinterpret_cast<const float4*>(sr + wstride + c);
                 }
                 if (c + 0 < dim) opt_elem<float>(opt, rc, w.x, a.x, b.x, g.x);
                 if (c + 1 < dim) opt_elem<float>(opt, rc, w.y, a.y, b.y, g.y);
                 if (c + 2 < dim) opt_elem<float>(opt, rc, w.z, a.z, b.z, g.z);
                 if (c + 3 < dim) opt_elem<float>(opt, rc, w.w, a.w, b.w, g.w);
-                *reinterpret_cast<float4*>(wr + c) = w;
-                if (nslots > 0) *reinterpret_cast<float4*>(sr + c) = a;
-                if (nslots > 1) *reinterpret_cast<float4*>(sr + wstride + c) = b;
-                *reinterpret_cast<float4*>(ar + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(gw + c) = w;
+                if (nslots > 0) *reinterpret_cast<float4*>(gs + c) = a;
+                if (nslots > 1) *reinterpret_cast<float4*>(gs + wstride + c) = b;
+                *reinterpret_cast<float4*>(ga + c) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (gl == 0) {
-                for (int i = 0; i < nsc; ++i) sr[(size_t)nslots * wstride + i] = nsc_v[i];
+                for (int i = 0; i < nsc; ++i) gs[(size_t)nslots * wstride + i] = nsc_v[i];
                 if (f == 2)   // pad words of a brand-new state row
-                    for (int i = nslots * wstride + nsc; i < sstride; ++i) sr[i] = 0.f;
+                    for (int i = nslots * wstride + nsc; i < sstride; ++i) gs[i] = 0.f;
             }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (fl) {
-            bulk_s2g(wloc + grow * (unsigned long long)wstride, wrow_s, wb);
-            bulk_s2g(T.state + grow * (unsigned long long)sstride, srow_s, sb);
-            bulk_s2g(accbase + (unsigned long long)gh * wstride, arow_s, wb);
-        }
-        bulk_commit();
-        bulk_wait_read();
         __syncwarp();
     }
 }

@@ -1,0 +1,423 @@
+// dense_kernels.cu -- the non-GEMM kernels of the fused dense step (DeepFM / Wide&Deep).
+//
+//   prep      X32 (pull output) -> bf16 MLP input A0 and its transpose A0T, FM field sums S,
+//             per-sample base logit (linear + FM + bias); cached ("sparse_as_dense") tables
+//             are gathered here
+//   head      final dot with w_out, sigmoid, BCE loss, dlogit, dZ_last (+ transpose), gradients
+//             of the small parameters, linear-term gradients of the sparse rows
+//   cachegrad scatter-add of the cached tables' gradient rows
+//   adagrad   tf.keras Adagrad over the flat fp32 parameter buffer + refresh of the bf16
+//             K-major weight copies (W and W^T) consumed by the tcgen05 GEMMs
+//   allreduce one-shot / two-shot sum over peer-mapped gradient buffers (NVLink P2P), fused
+//             with nothing else on purpose: it replaces the NCCL call of the reference's
+//             Horovod DistributedOptimizer (K5 in SURVEY 2.5)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace {
+
+thread_local std::string g_dense_err;
+
+struct PrepArgs {
+    float* X32; long long xs;            // [B, XS] fp32: server emb cols filled by pull
+    __nv_bfloat16* A0; __nv_bfloat16* A0T;   // [B, K0p], [K0p, B]
+    const long long* ids; int ncols;     // [B, ncols] int64
+    const float* dense; int nd;          // [B, nd]
+    const float* cache_emb; const float* cache_lin;   // [Vc, Dp], [Vc]
+    const int* cache_col; const long long* cache_off; int nc;   // cached features: id column, row offset
+    const float* wd; const float* bias;  // dense-linear weights [nd], global bias [1]
+    float* S; float* base;               // [B, Dp], [B]
+    int B, K0p, Dp, nf, ns, lin0, use_fm;   // lin0 = first column of the server linear terms in X32
+};
+
+// one CTA per 32 batch rows; thread t owns column (chunk*256 + t) of those 32 rows
+__global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
+    extern __shared__ float sm[];
+    float* sS = sm;                    // [32][Dp]
+    float* sq = sS + 32 * a.Dp;        // [32] sum of squares
+    float* sl = sq + 32;               // [32] linear sum
+    const int b0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * a.Dp + 64; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int emb_cols = a.nf * a.Dp, srv_cols = a.ns * a.Dp;
+    for (int col = threadIdx.x; col < a.K0p; col += blockDim.x) {
+        float v[32];
+        const bool is_emb = col < emb_cols;
+        const int d = is_emb ? col % a.Dp : 0;
+        int cj = -1;
+        if (is_emb && col >= srv_cols) cj = (col - srv_cols) / a.Dp;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int b = b0 + r;
+            float x = 0.f;
+            if (b < a.B) {
+                if (col < srv_cols) x = a.X32[(size_t)b * a.xs + col];
+                else if (is_emb) {
+                    long long id = a.ids[(size_t)b * a.ncols + a.cache_col[cj]];
+                    x = a.cache_emb[(size_t)(a.cache_off[cj] + id) * a.Dp + d];
+                    a.X32[(size_t)b * a.xs + col] = x;
+                } else if (col < emb_cols + a.nd) x = a.dense[(size_t)b * a.nd + (col - emb_cols)];
+                else if (col == a.K0p - 1) x = 1.f;
+            }
+            v[r] = x;
+        }
+        if (is_emb && a.use_fm) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                atomicAdd(&sS[r * a.Dp + d], v[r]);
+                atomicAdd(&sq[r], v[r] * v[r]);
+            }
+        }
+        if (col >= emb_cols && col < emb_cols + a.nd) {
+            const float w = a.wd[col - emb_cols];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) atomicAdd(&sl[r], v[r] * w);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
+            if (b0 + r < a.B) a.A0[(size_t)(b0 + r) * a.K0p + col] = h;
+            const uint16_t u = *reinterpret_cast<const uint16_t*>(&h);
+            if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
+        }
+        if (b0 + 31 < a.B) {
+            uint4* tp = reinterpret_cast<uint4*>(a.A0T + (size_t)col * a.B + b0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+            for (int r = 0; r < 32 && b0 + r < a.B; ++r)
+                a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
+        }
+    }
+    // linear terms: server rows (from X32) + cached rows
+    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc); i += blockDim.x) {
+        const int r = i / (a.ns + a.nc), j = i % (a.ns + a.nc), b = b0 + r;
+        if (b >= a.B) continue;
+        float x;
+        if (j < a.ns) x = a.X32[(size_t)b * a.xs + a.lin0 + j];
+        else {
+            long long id = a.ids[(size_t)b * a.ncols + a.cache_col[j - a.ns]];
+            x = a.cache_lin[a.cache_off[j - a.ns] + id];
+        }
+        atomicAdd(&sl[r], x);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * a.Dp; i += blockDim.x) {
+        const int r = i / a.Dp, b = b0 + r;
+        if (b < a.B) a.S[(size_t)b * a.Dp + (i % a.Dp)] = sS[i];
+    }
+    if (threadIdx.x < 32 && b0 + threadIdx.x < a.B) {
+        const int r = threadIdx.x;
+        float fm = 0.f;
+        if (a.use_fm) {
+            for (int d = 0; d < a.Dp; ++d) fm += sS[r * a.Dp + d] * sS[r * a.Dp + d];
+            fm = 0.5f * (fm - sq[r]);
+        }
+        a.base[b0 + r] = sl[r] + fm + a.bias[0];
+    }
+}
+
+struct HeadArgs {
+    const __nv_bfloat16* H; int Hp, ones_col;     // last hidden activation [B, Hp]
+    const float* wout;                            // [Hp] (ones_col entry = output bias)
+    const float* base; const float* labels;       // [B]
+    float* dlogit; float* loss;                   // [B], [1] (sum of per-sample loss / B)
+    __nv_bfloat16* dZ; __nv_bfloat16* dZT;        // [B, Hp], [Hp, B]
+    float* g_wout; float* g_wd; float* g_bias;    // gradients of the small parameters
+    const float* dense; int nd;
+    float* G32; long long xs; int lin0, ns;       // linear-term grads of server rows
+    const long long* ids; int ncols;
+    const int* cache_col; const long long* cache_off; int nc; float* g_cache_lin;
+    int B;
+    float grad_scale;                             // 1/B (mean loss)
+};
+
+__global__ void __launch_bounds__(256) exb_head_kernel(HeadArgs a) {
+    __shared__ float s_dl[32];
+    __shared__ float s_loss[8];
+    const int b0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float lsum = 0.f;
+    for (int r = warp; r < 32; r += 8) {          // 4 rows per warp
+        const int b = b0 + r;
+        float z = 0.f;
+        if (b < a.B) {
+            const __nv_bfloat16* h = a.H + (size_t)b * a.Hp;
+            for (int n = lane; n < a.Hp; n += 32) z += __bfloat162float(h[n]) * a.wout[n];
+        }
+        for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        if (lane == 0) {
+            float dl = 0.f;
+            if (b < a.B) {
+                z += a.base[b];
+                const float y = a.labels[b];
+                // numerically stable BCE with logits
+                const float l = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+                const float p = 1.f / (1.f + expf(-z));
+                dl = (p - y) * a.grad_scale;
+                a.dlogit[b] = dl;
+                lsum += l * a.grad_scale;
+            }
+            s_dl[r] = dl;
+        }
+    }
+    if (lane == 0) s_loss[warp] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_loss[i];
+        atomicAdd(a.loss, t);
+        float gb = 0.f;
+        for (int r = 0; r < 32; ++r) gb += s_dl[r];
+        atomicAdd(a.g_bias, gb);
+    }
+    // dZ = dl * wout * relu'(H), both layouts; g_wout
+    for (int n = threadIdx.x; n < a.Hp; n += blockDim.x) {
+        const float w = a.wout[n];
+        float gw = 0.f;
+        uint32_t pk[16];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int b = b0 + r;
+            float h = 0.f, dz = 0.f;
+            if (b < a.B) {
+                h = __bfloat162float(a.H[(size_t)b * a.Hp + n]);
+                gw += s_dl[r] * h;
+                if (h > 0.f && n != a.ones_col) dz = s_dl[r] * w;
+                a.dZ[(size_t)b * a.Hp + n] = __float2bfloat16_rn(dz);
+            }
+            const __nv_bfloat16 hb = __float2bfloat16_rn(dz);
+            const uint16_t u = *reinterpret_cast<const uint16_t*>(&hb);
+            if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
+        }
+        if (b0 + 31 < a.B) {
+            uint4* tp = reinterpret_cast<uint4*>(a.dZT + (size_t)n * a.B + b0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+            for (int r = 0; r < 32 && b0 + r < a.B; ++r) {
+                const uint16_t u = (pk[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+                a.dZT[(size_t)n * a.B + b0 + r] = *reinterpret_cast<const __nv_bfloat16*>(&u);
+            }
+        }
+        atomicAdd(&a.g_wout[n], gw);
+    }
+    // linear-term gradients: server rows -> G32, cached rows -> dense grad, dense-linear weights
+    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc); i += blockDim.x) {
+        const int r = i / (a.ns + a.nc), j = i % (a.ns + a.nc), b = b0 + r;
+        if (b >= a.B) continue;
+        if (j < a.ns) a.G32[(size_t)b * a.xs + a.lin0 + j] = s_dl[r];
+        else {
+            long long id = a.ids[(size_t)b * a.ncols + a.cache_col[j - a.ns]];
+            atomicAdd(&a.g_cache_lin[a.cache_off[j - a.ns] + id], s_dl[r]);
+        }
+    }
+    for (int j = threadIdx.x; j < a.nd; j += blockDim.x) {
+        float g = 0.f;
+        for (int r = 0; r < 32 && b0 + r < a.B; ++r) g += s_dl[r] * a.dense[(size_t)(b0 + r) * a.nd + j];
+        atomicAdd(&a.g_wd[j], g);
+    }
+}
+
+// scatter-add the gradient rows of the cached (replicated) embedding tables
+__global__ void exb_cachegrad_kernel(const float* G32, long long xs, int col0, int Dp, const long long* ids, int ncols,
+                                     const int* cache_col, const long long* cache_off, int nc, float* g_cache_emb,
+                                     int B) {
+    const int chunks = Dp / 4;
+    const long long total = (long long)B * nc * chunks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % chunks) * 4;
+        const int j = (int)((i / chunks) % nc);
+        const int b = (int)(i / ((long long)chunks * nc));
+        const float4 g = *reinterpret_cast<const float4*>(G32 + (size_t)b * xs + col0 + j * Dp + c);
+        const long long id = ids[(size_t)b * ncols + cache_col[j]];
+        float* dst = g_cache_emb + (size_t)(cache_off[j] + id) * Dp + c;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+    }
+}
+
+// Adagrad on the flat fp32 buffer (tf.keras semantics: accum += g^2; w -= lr * g / (sqrt(accum) + eps))
+__global__ void exb_adagrad_flat_kernel(float* theta, float* accum, const float* grad, long long n, float lr, float eps) {
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < n;
+         i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < n) {
+            float4 g = *reinterpret_cast<const float4*>(grad + i);
+            float4 a = *reinterpret_cast<float4*>(accum + i);
+            float4 w = *reinterpret_cast<float4*>(theta + i);
+            a.x += g.x * g.x; a.y += g.y * g.y; a.z += g.z * g.z; a.w += g.w * g.w;
+            w.x -= lr * g.x / (sqrtf(a.x) + eps); w.y -= lr * g.y / (sqrtf(a.y) + eps);
+            w.z -= lr * g.z / (sqrtf(a.z) + eps); w.w -= lr * g.w / (sqrtf(a.w) + eps);
+            *reinterpret_cast<float4*>(accum + i) = a;
+            *reinterpret_cast<float4*>(theta + i) = w;
+        } else {
+            for (long long k = i; k < n; ++k) {
+                float g = grad[k], a = accum[k] + g * g;
+                accum[k] = a;
+                theta[k] -= lr * g / (sqrtf(a) + eps);
+            }
+        }
+    }
+}
+
+// W fp32 [R, C] -> Wb bf16 [R, C] and WTb bf16 [C, R] (32x32 smem tile transpose)
+__global__ void exb_refresh_bf16_kernel(const float* W, __nv_bfloat16* Wb, __nv_bfloat16* WTb, int R, int C) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        float v = (r < R && c < C) ? W[(size_t)r * C + c] : 0.f;
+        tile[i][threadIdx.x] = v;
+        if (r < R && c < C) Wb[(size_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) WTb[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+
+// ---- P2P all-reduce (sum) over peer-mapped buffers -------------------------------------
+struct ArArgs {
+    float* buf[8];          // every rank's gradient buffer (peer mapped), index = rank
+    unsigned* flags[8];     // every rank's flag array [8]
+    unsigned* epoch;        // local
+    int* status;
+    long long n;
+    int W, rank;
+};
+
+__device__ __forceinline__ void ar_barrier(const ArArgs& a) {   // executed by CTA 0 only
+    __threadfence_system();
+    __syncthreads();
+    const unsigned e = *(volatile unsigned*)a.epoch + 1;
+    __syncthreads();
+    if ((int)threadIdx.x < a.W) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.flags[threadIdx.x][a.rank]), "r"(e) : "memory");
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (unsigned it = 0;; ++it) {
+            unsigned v;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&a.flags[a.rank][threadIdx.x]) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if ((it & 255u) == 255u) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) { atomicCAS(a.status, 0, 2); break; }
+            }
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned*)a.epoch = e;
+    __threadfence_system();
+    __syncthreads();
+}
+
+// Five launches, stream order is the grid-wide barrier:
+//   barrier | reduce-scatter (peer LOADS of this rank's slice from every peer) | barrier |
+//   all-gather (peer STORES of the reduced slice into every peer) | barrier
+__global__ void exb_ar_barrier_kernel(ArArgs a) { ar_barrier(a); }
+
+__global__ void __launch_bounds__(256) exb_ar_reduce_scatter_kernel(ArArgs a, float* scratch) {
+    const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
+    const long long lo = per * a.rank, hi = min(a.n, lo + per);
+    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
+         i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < a.W; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(a.buf[r] + i);   // peer load over NVLink
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(scratch + (i - lo)) = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) exb_ar_all_gather_kernel(ArArgs a, const float* scratch) {
+    const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
+    const long long lo = per * a.rank, hi = min(a.n, lo + per);
+    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
+         i += (long long)gridDim.x * blockDim.x * 4) {
+        const float4 s = *reinterpret_cast<const float4*>(scratch + (i - lo));
+#pragma unroll 8
+        for (int r = 0; r < a.W; ++r) *reinterpret_cast<float4*>(a.buf[r] + i) = s;   // peer store
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* exb_dense_last_error() { return g_dense_err.c_str(); }
+
+int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
+    PrepArgs a = *reinterpret_cast<const PrepArgs*>(args);
+    size_t smem = (32 * (size_t)Dp + 64) * 4;
+    exb_prep_kernel<<<(B + 31) / 32, 256, smem, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+int exb_prep_args_size() { return (int)sizeof(PrepArgs); }
+int exb_head(const void* args, int B, uint64_t stream) {
+    HeadArgs a = *reinterpret_cast<const HeadArgs*>(args);
+    exb_head_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+int exb_head_args_size() { return (int)sizeof(HeadArgs); }
+int exb_cachegrad(uint64_t G32, long long xs, int col0, int Dp, uint64_t ids, int ncols, uint64_t cache_col,
+                  uint64_t cache_off, int nc, uint64_t g_cache_emb, int B, uint64_t stream) {
+    if (nc == 0) return 0;
+    long long total = (long long)B * nc * (Dp / 4);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    exb_cachegrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)G32, xs, col0, Dp, (const long long*)ids,
+                                                                 ncols, (const int*)cache_col, (const long long*)cache_off,
+                                                                 nc, (float*)g_cache_emb, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+int exb_adagrad_flat(uint64_t theta, uint64_t accum, uint64_t grad, long long n, float lr, float eps, uint64_t stream) {
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid < 1) grid = 1;
+    exb_adagrad_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)theta, (float*)accum, (const float*)grad, n, lr, eps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+int exb_refresh_bf16(uint64_t W, uint64_t Wb, uint64_t WTb, int R, int C, uint64_t stream) {
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    exb_refresh_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float*)W, (__nv_bfloat16*)Wb, (__nv_bfloat16*)WTb, R, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+// all-reduce (sum, in place) of a flat fp32 buffer of n elements (n % 4 == 0, 16-byte aligned)
+// that every rank has peer-mapped; bufs/flags: W pointers each; epoch/status: local words.
+int exb_allreduce_sum(const uint64_t* bufs, const uint64_t* flags, uint64_t epoch, uint64_t status, uint64_t scratch,
+                      long long n, int W, int rank, int ctas, uint64_t stream) {
+    ArArgs a;
+    for (int i = 0; i < 8; ++i) { a.buf[i] = i < W ? (float*)bufs[i] : nullptr; a.flags[i] = i < W ? (unsigned*)flags[i] : nullptr; }
+    a.epoch = (unsigned*)epoch; a.status = (int*)status; a.n = n; a.W = W; a.rank = rank;
+    if (ctas < 1) ctas = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
+    exb_ar_reduce_scatter_kernel<<<ctas, 256, 0, st>>>(a, (float*)scratch);
+    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
+    exb_ar_all_gather_kernel<<<ctas, 256, 0, st>>>(a, (const float*)scratch);
+    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+}  // extern "C"

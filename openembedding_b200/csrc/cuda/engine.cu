@@ -564,6 +564,19 @@ int exb_table_rehash(void* h, int ti, uint64_t new_capacity) {
     return 0;
 }
 
+// ---- raw (cudaMalloc-owned, IPC-exportable) buffers for python-side peer-mapped tensors
+uint64_t exb_raw_alloc(int device, uint64_t nbytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return 0;
+    void* p = nullptr;
+    nbytes = align_up(nbytes, 2u << 20);
+    cudaError_t err = cudaMalloc(&p, nbytes);
+    if (err != cudaSuccess) { fail("cudaMalloc", err); return 0; }
+    cudaMemset(p, 0, nbytes);
+    cudaDeviceSynchronize();
+    return (uint64_t)p;
+}
+int exb_raw_free(uint64_t ptr) { CK(cudaFree((void*)ptr)); return 0; }
+
 // ---- IPC
 int exb_ipc_get_handle(uint64_t ptr, char* out64) {
     cudaIpcMemHandle_t hdl;

@@ -57,7 +57,7 @@ class FusedEmbeddings(nn.Module):
     column (`col`), e.g. the dim-D and the dim-1 table of one sparse feature.
     """
 
-    def __init__(self, specs, batch, optimizer, num_shards=None, ncols=None):
+    def __init__(self, specs, batch, optimizer, num_shards=None, ncols=None, feat_offsets=None, io_stride=None):
         super().__init__()
         ctx = get_context()
         self.ctx = ctx
@@ -70,7 +70,14 @@ class FusedEmbeddings(nn.Module):
             ctx.set_initializer(m, s.get("initializer", {"category": "constant", "value": 0.0}))
             ctx.set_optimizer(m, optimizer)
             self.metas.append(m)
-        self.group = ctx.backend.make_group(self.metas, batch, feat_cols=[s["col"] for s in specs], ncols=ncols)
+        if feat_offsets is not None:
+            ctx.backend.ensure_allocated(self.metas)
+            self.group = ctx.backend.engine.make_plan([m.handle for m in self.metas], batch, feat_offsets=feat_offsets,
+                                                      io_stride=io_stride, feat_cols=[s["col"] for s in specs],
+                                                      ncols=ncols)
+            ctx.backend.engine.connect(ctx.backend.group)
+        else:
+            self.group = ctx.backend.make_group(self.metas, batch, feat_cols=[s["col"] for s in specs], ncols=ncols)
         self.slices = self.group.feature_slices()
         self.io_stride = self.group.io_stride
         self.anchor = nn.Parameter(torch.zeros(1, device=ctx.device))  # keeps autograd attached

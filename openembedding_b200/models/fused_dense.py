@@ -1,0 +1,353 @@
+"""Fused DeepFM / Wide&Deep training step on hand-written sm_100a kernels only.
+
+Per step and per GPU (15 launches, captured in one CUDA graph by ``FusedTrainer``):
+
+    pull (peer loads, UBLKCP)            sparse_kernels.cuh
+    prep                                 dense_kernels.cu   X32 -> A0, A0^T (bf16), FM sums, base logit
+    3x GEMM fwd  (tcgen05, relu, ones)   gemm_tcgen05.cu
+    head         (loss, dlogit, dZ_L)    dense_kernels.cu
+    3x GEMM dX   (tcgen05, relu mask / FM-fused fp32 embedding gradient)
+    3x GEMM dW   (tcgen05, split-K, fp32 red.add)
+    cachegrad, push_update (P2P dispatch + combine + sparse optimizer), P2P all-reduce,
+    Adagrad(flat) + bf16 weight refresh
+
+No cuBLAS, no NCCL, no torch op on the step. Biases are folded into the GEMMs through a
+constant "ones" column, so a layer is exactly one GEMM in each direction.
+
+Model definition = DeepCTR's DeepFM / WDL as used by the reference benchmark
+(test/benchmark/criteo_deepctr.py:243-282); see ``models/ctr.py`` for the eager version
+of the same architecture (used as the numerical reference in tests).
+"""
+import ctypes
+import math
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+from .. import _native
+from ..context import get_context
+from ..ops import gemm as G
+
+
+class _PrepArgs(ctypes.Structure):
+    _fields_ = [("X32", c_void_p), ("xs", c_longlong), ("A0", c_void_p), ("A0T", c_void_p), ("ids", c_void_p),
+                ("ncols", c_int), ("dense", c_void_p), ("nd", c_int), ("cache_emb", c_void_p),
+                ("cache_lin", c_void_p), ("cache_col", c_void_p), ("cache_off", c_void_p), ("nc", c_int),
+                ("wd", c_void_p), ("bias", c_void_p), ("S", c_void_p), ("base", c_void_p), ("B", c_int),
+                ("K0p", c_int), ("Dp", c_int), ("nf", c_int), ("ns", c_int), ("lin0", c_int), ("use_fm", c_int)]
+
+
+class _HeadArgs(ctypes.Structure):
+    _fields_ = [("H", c_void_p), ("Hp", c_int), ("ones_col", c_int), ("wout", c_void_p), ("base", c_void_p),
+                ("labels", c_void_p), ("dlogit", c_void_p), ("loss", c_void_p), ("dZ", c_void_p), ("dZT", c_void_p),
+                ("g_wout", c_void_p), ("g_wd", c_void_p), ("g_bias", c_void_p), ("dense", c_void_p), ("nd", c_int),
+                ("G32", c_void_p), ("xs", c_longlong), ("lin0", c_int), ("ns", c_int), ("ids", c_void_p),
+                ("ncols", c_int), ("cache_col", c_void_p), ("cache_off", c_void_p), ("nc", c_int),
+                ("g_cache_lin", c_void_p), ("B", c_int), ("grad_scale", c_float)]
+
+
+def _r(x, m):
+    return (x + m - 1) // m * m
+
+
+_proto = False
+
+
+def _lib():
+    global _proto
+    lib = _native.cuda()
+    if not _proto:
+        u64 = ctypes.c_uint64
+        lib.exb_prep.restype = c_int
+        lib.exb_prep.argtypes = [c_void_p, c_int, c_int, u64]
+        lib.exb_head.restype = c_int
+        lib.exb_head.argtypes = [c_void_p, c_int, u64]
+        lib.exb_prep_args_size.restype = c_int
+        lib.exb_head_args_size.restype = c_int
+        lib.exb_cachegrad.restype = c_int
+        lib.exb_cachegrad.argtypes = [u64, c_longlong, c_int, c_int, u64, c_int, u64, u64, c_int, u64, c_int, u64]
+        lib.exb_adagrad_flat.restype = c_int
+        lib.exb_adagrad_flat.argtypes = [u64, u64, u64, c_longlong, c_float, c_float, u64]
+        lib.exb_refresh_bf16.restype = c_int
+        lib.exb_refresh_bf16.argtypes = [u64, u64, u64, c_int, c_int, u64]
+        lib.exb_allreduce_sum.restype = c_int
+        lib.exb_allreduce_sum.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64), u64, u64, u64, c_longlong, c_int,
+                                          c_int, c_int, u64]
+        lib.exb_dense_last_error.restype = ctypes.c_char_p
+        assert lib.exb_prep_args_size() == ctypes.sizeof(_PrepArgs), "PrepArgs ABI mismatch"
+        assert lib.exb_head_args_size() == ctypes.sizeof(_HeadArgs), "HeadArgs ABI mismatch"
+        _proto = True
+    return lib
+
+
+def _ck(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s: %s" % (what, _lib().exb_dense_last_error().decode()))
+
+
+class FusedCTR:
+    """DeepFM (use_fm=True) or Wide&Deep (use_fm=False) with the whole step on own kernels."""
+
+    def __init__(self, vocab_sizes, num_dense=13, embedding_dim=64, model="deepfm", batch=4096, hidden=None,
+                 sparse_optimizer=None, cache_threshold=0, lr=0.001, initial_accumulator_value=0.1, eps=1e-7,
+                 num_shards=None, dw_splits=8, seed=0):
+        from .ctr import FusedEmbeddings
+        ctx = get_context()
+        if ctx.device.type != "cuda":
+            raise RuntimeError("FusedCTR runs on the CUDA engine only (use models.ctr.CTRModel on CPU)")
+        assert batch % 128 == 0, "the fused dense path needs batch % 128 == 0"
+        self.ctx, self.dev, self.lib = ctx, ctx.device, _lib()
+        self.model = model.lower()
+        assert self.model in ("deepfm", "wdl")
+        self.use_fm = self.model == "deepfm"
+        self.B, self.nd, self.D = batch, num_dense, embedding_dim
+        self.Dp = _r(embedding_dim, 4)
+        self.vocab = list(vocab_sizes)
+        self.nf = len(self.vocab)
+        if hidden is None:
+            hidden = (400, 400, 400) if self.use_fm else (512, 256, 128, 32)
+        self.hidden = list(hidden)
+        self.Hp = [_r(h + 1, 64) for h in self.hidden]
+        self.lr, self.eps, self.dw_splits = lr, eps, dw_splits
+        self.cached = [f for f, v in enumerate(self.vocab) if 0 < v < cache_threshold]
+        self.server = [f for f in range(self.nf) if f not in self.cached]
+        self.ns, self.nc = len(self.server), len(self.cached)
+        nf, Dp = self.nf, self.Dp
+        self.K0p = _r(nf * Dp + num_dense + 1, 64)
+        self.lin0 = self.K0p
+        self.XS = _r(self.K0p + self.ns, 4)
+        sparse_optimizer = sparse_optimizer or {"category": "adagrad"}
+        zero = {"category": "constant", "value": 0.0}
+        specs = [{"vocab": self.vocab[f], "dim": embedding_dim, "col": f, "initializer": zero} for f in self.server]
+        specs += [{"vocab": self.vocab[f], "dim": 1, "col": f, "initializer": zero} for f in self.server]
+        offs = [j * Dp for j in range(self.ns)] + [self.lin0 + j for j in range(self.ns)]
+        self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards, ncols=nf,
+                                      feat_offsets=offs, io_stride=self.XS)
+        self.group = self.sparse.group
+        dev = self.dev
+        f32, bf16 = torch.float32, torch.bfloat16
+        # ---- flat parameter buffer
+        segs, off = {}, 0
+        dims = [self.K0p] + self.Hp
+        for l in range(len(self.hidden)):
+            n = self.Hp[l] * dims[l]
+            segs["W%d" % l] = (off, n)
+            off = _r(off + n, 4)
+        L = len(self.hidden)
+        for name, n in (("wout", self.Hp[-1]), ("wd", max(num_dense, 1)), ("bias", 1)):
+            segs[name] = (off, n)
+            off = _r(off + n, 4)
+        vc = sum(self.vocab[f] for f in self.cached)
+        self.cache_rows = vc
+        segs["cache_emb"] = (off, vc * Dp)
+        off = _r(off + vc * Dp, 4)
+        segs["cache_lin"] = (off, vc)
+        off = _r(off + max(vc, 1), 4)
+        self.segs, self.n_theta = segs, off
+        self.theta = torch.zeros(off, dtype=f32, device=dev)
+        self.accum = torch.full((off,), float(initial_accumulator_value), dtype=f32, device=dev)
+        self.gtheta = torch.zeros(off, dtype=f32, device=dev)
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+        fan_in = [nf * embedding_dim + num_dense] + self.hidden
+        for l in range(L):
+            W = self.view("W%d" % l).view(self.Hp[l], dims[l])
+            h_out = self.hidden[l]
+            std = math.sqrt(2.0 / (fan_in[l] + h_out))            # glorot normal (DeepCTR DNN default)
+            real_in = nf * Dp + num_dense if l == 0 else self.hidden[l - 1]
+            blk = torch.randn(h_out, real_in, generator=gen) * std
+            if l == 0 and Dp != embedding_dim:                     # zero the weights that face pad columns
+                m = torch.ones(nf, Dp)
+                m[:, embedding_dim:] = 0
+                blk[:, :nf * Dp] *= m.reshape(-1)
+            W[:h_out, :real_in] = blk.to(dev)
+        self.view("wout")[: self.hidden[-1]] = (torch.randn(self.hidden[-1], generator=gen)
+                                                 * math.sqrt(2.0 / (self.hidden[-1] + 1))).to(dev)
+        if num_dense:
+            self.view("wd")[:num_dense] = (torch.randn(num_dense, generator=gen) * math.sqrt(2.0 / (num_dense + 1))).to(dev)
+        # ---- bf16 K-major weight copies
+        self.Wb = [torch.zeros(self.Hp[l], dims[l], dtype=bf16, device=dev) for l in range(L)]
+        self.WTb = [torch.zeros(dims[l], self.Hp[l], dtype=bf16, device=dev) for l in range(L)]
+        # ---- activations
+        B = batch
+        self.X32 = torch.zeros(B, self.XS, dtype=f32, device=dev)
+        self.G32 = torch.zeros(B, self.XS, dtype=f32, device=dev)
+        self.A0 = torch.zeros(B, self.K0p, dtype=bf16, device=dev)
+        self.A0T = torch.zeros(self.K0p, B, dtype=bf16, device=dev)
+        self.H = [torch.zeros(B, hp, dtype=bf16, device=dev) for hp in self.Hp]
+        self.HT = [torch.zeros(hp, B, dtype=bf16, device=dev) for hp in self.Hp]
+        self.dZ = [torch.zeros(B, hp, dtype=bf16, device=dev) for hp in self.Hp]
+        self.dZT = [torch.zeros(hp, B, dtype=bf16, device=dev) for hp in self.Hp]
+        self.S = torch.zeros(B, Dp, dtype=f32, device=dev)
+        self.base = torch.zeros(B, dtype=f32, device=dev)
+        self.dlogit = torch.zeros(B, dtype=f32, device=dev)
+        self.loss = torch.zeros(1, dtype=f32, device=dev)
+        offs_c, o = [], 0
+        for f in self.cached:
+            offs_c.append(o)
+            o += self.vocab[f]
+        self.cache_col = torch.tensor(self.cached or [0], dtype=torch.int32, device=dev)
+        self.cache_off = torch.tensor(offs_c or [0], dtype=torch.int64, device=dev)
+        self._ar = None
+        if ctx.world > 1:
+            from ..ops.p2p_allreduce import P2PAllReduce
+            self._ar = P2PAllReduce(ctx, self.gtheta)
+        self.refresh_weights()
+        torch.cuda.synchronize(dev)
+
+    # ---- helpers
+    def view(self, name):
+        o, n = self.segs[name]
+        return self.theta[o:o + n]
+
+    def gview(self, name):
+        o, n = self.segs[name]
+        return self.gtheta[o:o + n]
+
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def refresh_weights(self):
+        dims = [self.K0p] + self.Hp
+        for l in range(len(self.hidden)):
+            _ck(self.lib.exb_refresh_bf16(self.view("W%d" % l).data_ptr(), self.Wb[l].data_ptr(),
+                                          self.WTb[l].data_ptr(), self.Hp[l], dims[l], self._st()), "refresh_bf16")
+
+    # ---- one training step (all launches on the current stream)
+    def forward_backward(self, ids, dense, labels, update=True):
+        B, L, lib, st = self.B, len(self.hidden), self.lib, self._st()
+        assert ids.shape == (B, self.nf) and ids.dtype == torch.int64 and ids.is_contiguous()
+        self.gtheta.zero_()
+        self.loss.zero_()
+        self.group.pull(ids, out=self.X32)
+        pa = _PrepArgs(self.X32.data_ptr(), self.XS, self.A0.data_ptr(), self.A0T.data_ptr(), ids.data_ptr(), self.nf,
+                       dense.data_ptr(), self.nd, self.view("cache_emb").data_ptr(), self.view("cache_lin").data_ptr(),
+                       self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc, self.view("wd").data_ptr(),
+                       self.view("bias").data_ptr(), self.S.data_ptr(), self.base.data_ptr(), B, self.K0p, self.Dp,
+                       self.nf, self.ns, self.lin0, int(self.use_fm))
+        _ck(lib.exb_prep(ctypes.byref(pa), B, self.Dp, st), "prep")
+        dims = [self.K0p] + self.Hp
+        src = self.A0
+        for l in range(L):
+            G.gemm_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
+                      ones_col=self.Hp[l] - 1, outT=self.HT[l] if l < L - 1 else None, stream=st)
+            src = self.H[l]
+        ha = _HeadArgs(self.H[-1].data_ptr(), self.Hp[-1], self.Hp[-1] - 1, self.view("wout").data_ptr(),
+                       self.base.data_ptr(), labels.data_ptr(), self.dlogit.data_ptr(), self.loss.data_ptr(),
+                       self.dZ[-1].data_ptr(), self.dZT[-1].data_ptr(), self.gview("wout").data_ptr(),
+                       self.gview("wd").data_ptr(), self.gview("bias").data_ptr(), dense.data_ptr(), self.nd,
+                       self.G32.data_ptr(), self.XS, self.lin0, self.ns, ids.data_ptr(), self.nf,
+                       self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
+                       self.gview("cache_lin").data_ptr(), B, 1.0 / B)
+        _ck(lib.exb_head(ctypes.byref(ha), B, st), "head")
+        for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
+            G.gemm_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
+                      ones_col=self.Hp[l - 1] - 1, outT=self.dZT[l - 1], mask=self.H[l - 1], stream=st)
+        G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
+                  S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
+        for l in range(L):                 # dW_l = dZ_l^T @ H_{l-1}
+            prevT = self.A0T if l == 0 else self.HT[l - 1]
+            gW = self.gview("W%d" % l).view(self.Hp[l], dims[l])
+            G.gemm_nt(self.dZT[l], prevT, self.Hp[l], dims[l], B, gW, mode=G.EPI_DW, splits=self.dw_splits, stream=st)
+        if self.nc:
+            _ck(lib.exb_cachegrad(self.G32.data_ptr(), self.XS, self.ns * self.Dp, self.Dp, ids.data_ptr(), self.nf,
+                                  self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
+                                  self.gview("cache_emb").data_ptr(), B, st), "cachegrad")
+        if update:
+            self.group.push_update(ids, self.G32)
+            if self._ar is not None:
+                self._ar()
+            _ck(lib.exb_adagrad_flat(self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr(), self.n_theta,
+                                     self.lr, self.eps, st), "adagrad")
+            self.refresh_weights()
+        return self.loss
+
+    own_kernels_per_step = 15
+
+    # ---- fp32 torch reference of the dense math on the current X32 (tests)
+    def reference(self, ids, dense, labels):
+        """returns (loss, grads dict) computed with torch autograd in fp32 from the same
+        parameters and the same pulled embeddings (self.X32 after a forward)."""
+        B, nf, Dp, L = self.B, self.nf, self.Dp, len(self.hidden)
+        theta = self.theta.detach().clone().requires_grad_(True)
+        X = self.X32.detach().clone()
+        emb = X[:, :nf * Dp].clone()
+        if self.nc:
+            ce = theta[self.segs["cache_emb"][0]:self.segs["cache_emb"][0] + self.cache_rows * Dp].view(-1, Dp)
+            cid = ids[:, self.cache_col.long()] + self.cache_off
+            emb = torch.cat([emb[:, :self.ns * Dp], ce[cid].reshape(B, -1)], dim=1)
+        emb = emb.detach().requires_grad_(True) if not self.nc else emb
+        emb_leaf = X[:, :self.ns * Dp].clone().requires_grad_(True)
+        if self.nc:
+            emb = torch.cat([emb_leaf, ce[cid].reshape(B, -1)], dim=1)
+        else:
+            emb = emb_leaf
+        lin_leaf = X[:, self.lin0:self.lin0 + self.ns].clone().requires_grad_(True)
+        lin = lin_leaf.sum(1)
+        if self.nc:
+            cl = theta[self.segs["cache_lin"][0]:self.segs["cache_lin"][0] + self.cache_rows]
+            lin = lin + cl[cid].sum(1)
+        wd = theta[self.segs["wd"][0]:self.segs["wd"][0] + self.nd]
+        bias = theta[self.segs["bias"][0]]
+        z = lin + dense @ wd + bias
+        if self.use_fm:
+            e = emb.view(B, nf, Dp)
+            s = e.sum(1)
+            z = z + 0.5 * (s * s - (e * e).sum(1)).sum(1)
+        ones = torch.ones(B, 1, device=self.dev)
+        dims = [self.K0p] + self.Hp
+        pad0 = self.K0p - 1 - nf * Dp - self.nd
+        h = torch.cat([emb, dense, torch.zeros(B, pad0, device=self.dev), ones], dim=1)
+        for l in range(L):
+            o, n = self.segs["W%d" % l]
+            W = theta[o:o + n].view(self.Hp[l], dims[l])
+            h = torch.relu(h.to(torch.bfloat16).float() @ W.to(torch.bfloat16).float().t())
+            h = torch.cat([h[:, :-1], ones], dim=1)
+        o, n = self.segs["wout"]
+        z = z + h.to(torch.bfloat16).float() @ theta[o:o + n]
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(z, labels)
+        loss.backward()
+        return loss.detach(), {"theta": theta.grad, "emb": emb_leaf.grad, "lin": lin_leaf.grad}
+
+
+class FusedTrainer:
+    """CUDA-graph driver for ``FusedCTR`` with the same interface as ``models.trainer.Trainer``."""
+
+    def __init__(self, model, use_graph=True):
+        self.m, self.ctx = model, model.ctx
+        self.device, self.world = model.dev, model.ctx.world
+        self.use_graph = use_graph
+        self.graph, self._static = None, None
+        self._ar = model._ar
+
+    def step(self, ids, dense, labels):
+        if not self.use_graph:
+            return self.m.forward_backward(ids, dense, labels)
+        if self.graph is None:
+            self._capture(ids, dense, labels)
+        s = self._static
+        if ids.data_ptr() != s["ids"].data_ptr():
+            s["ids"].copy_(ids, non_blocking=True)
+            s["dense"].copy_(dense, non_blocking=True)
+            s["labels"].copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return s["loss"]
+
+    def _capture(self, ids, dense, labels):
+        s = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.ctx.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+        self.graph, self._static = g, s
+
+    def make_pipeline(self, batch, num_sparse, num_dense):
+        from .trainer import _Pipeline
+        return _Pipeline(self, batch, num_sparse, num_dense)
