@@ -39,6 +39,8 @@ def parse():
     p.add_argument("--optimizer", default="adagrad")
     p.add_argument("--cache", type=int, default=4096, help="replicate tables smaller than this (reference --cache)")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--engine", default="auto", choices=["auto", "fused", "eager"],
+                   help="fused: every kernel of the step is ours (tcgen05 GEMMs ...); eager: torch dense ops")
     p.add_argument("--allreduce", default="auto")
     p.add_argument("--skew", type=float, default=1.0, help="0 = uniform ids, 1 = log-uniform (Zipf-like)")
     p.add_argument("--pool", type=int, default=16, help="distinct pre-generated batches cycled through")
@@ -138,9 +140,18 @@ def main():
     vocab = {"criteo1tb_20m": CRITEO_1TB_VOCAB_20M, "kaggle": CRITEO_KAGGLE_VOCAB,
              "tiny": [min(v, 10007) for v in CRITEO_KAGGLE_VOCAB]}[a.vocab]
     torch.manual_seed(1234)
-    model = CTRModel(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
-                     sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
-    trainer = Trainer(model, use_graph=not a.no_graph, allreduce=a.allreduce)
+    engine = a.engine
+    if engine == "auto":
+        engine = "fused" if (a.model in ("deepfm", "wdl") and a.batch % 128 == 0) else "eager"
+    if engine == "fused":
+        from openembedding_b200.models.fused_dense import FusedCTR, FusedTrainer
+        model = FusedCTR(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
+                         sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
+        trainer = FusedTrainer(model, use_graph=not a.no_graph)
+    else:
+        model = CTRModel(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
+                         sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
+        trainer = Trainer(model, use_graph=not a.no_graph, allreduce=a.allreduce)
     dev = ctx.device
     host = make_batches(torch, vocab, 13, a.batch, a.pool, a.skew, 1000 + rank, dev)
     devb = [(i.to(dev), d.to(dev), l.to(dev)) for i, d, l in host]
@@ -202,7 +213,10 @@ def main():
         value = gb * a.steps / (ms / 1e3)
         e2e_value = gb * a.steps / (e2e_ms / 1e3)
         pub = PUBLISHED_KIPS.get((a.model, a.dim), {}).get(world)
-        own_kernels_per_step = 2 + (1 if (world > 1 and trainer._ar is not None) else 0)
+        if engine == "fused":
+            own_kernels_per_step = model.kernels_per_step()
+        else:
+            own_kernels_per_step = 2 + (5 if (world > 1 and trainer._ar is not None) else 0)
         rows = sum(vocab)
         line = {
             "metric": "samples/sec (whole job, device-timed, max over ranks) %s Criteo dim %d" % (a.model, a.dim),
@@ -213,7 +227,7 @@ def main():
             "config": {"model": "%s (DeepCTR architecture), emb dim %d, %s sparse / Adagrad dense" % (a.model, a.dim, a.optimizer),
                        "global_batch": gb, "seq_len": 1, "parallelism": "dp%d + row-sharded embeddings (id %% %d) over NVLink" % (world, world),
                        "vocab_rows_total": rows, "tables_fp32_gb": round(rows * (a.dim + 1) * 4 * 2 / 2 ** 30, 1),
-                       "cache_threshold": a.cache, "cuda_graph": not a.no_graph,
+                       "cache_threshold": a.cache, "cuda_graph": not a.no_graph, "engine": engine,
                        "l2_policy": "inputs larger than L2: %d distinct random batches over a %.0f GB table working set" % (
                            a.pool, rows * (a.dim + 1) * 8 / 2 ** 30)},
             "clocks": clocks,

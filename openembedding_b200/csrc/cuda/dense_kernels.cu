@@ -33,15 +33,14 @@ struct PrepArgs {
     int B, K0p, Dp, nf, ns, lin0, use_fm;   // lin0 = first column of the server linear terms in X32
 };
 
-// one CTA per 32 batch rows; thread t owns column (chunk*256 + t) of those 32 rows
+// one CTA per 32 batch rows.
+//  phase A: thread t owns column (chunk*256 + t) of those 32 rows: gathers cached rows / dense
+//           features / the ones column, writes A0 (row major) and A0T (batch major, 64-byte runs)
+//  phase B: FM field sums with float4 loads (one thread per (row, 4 dims)), linear terms
 __global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
-    extern __shared__ float sm[];
-    float* sS = sm;                    // [32][Dp]
-    float* sq = sS + 32 * a.Dp;        // [32] sum of squares
-    float* sl = sq + 32;               // [32] linear sum
+    __shared__ float sq[32], sfm[32], sl[32];
     const int b0 = blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * a.Dp + 64; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
+    if (threadIdx.x < 32) { sq[threadIdx.x] = 0.f; sfm[threadIdx.x] = 0.f; sl[threadIdx.x] = 0.f; }
     const int emb_cols = a.nf * a.Dp, srv_cols = a.ns * a.Dp;
     for (int col = threadIdx.x; col < a.K0p; col += blockDim.x) {
         float v[32];
@@ -64,18 +63,6 @@ __global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
             }
             v[r] = x;
         }
-        if (is_emb && a.use_fm) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                atomicAdd(&sS[r * a.Dp + d], v[r]);
-                atomicAdd(&sq[r], v[r] * v[r]);
-            }
-        }
-        if (col >= emb_cols && col < emb_cols + a.nd) {
-            const float w = a.wd[col - emb_cols];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) atomicAdd(&sl[r], v[r] * w);
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
@@ -93,31 +80,44 @@ __global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
                 a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
         }
     }
-    // linear terms: server rows (from X32) + cached rows
-    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc); i += blockDim.x) {
-        const int r = i / (a.ns + a.nc), j = i % (a.ns + a.nc), b = b0 + r;
+    __syncthreads();   // cached columns of X32 written above are read below (same CTA)
+    const int q4 = a.Dp / 4;
+    for (int i = threadIdx.x; i < 32 * q4; i += blockDim.x) {
+        const int r = i / q4, c = (i % q4) * 4, b = b0 + r;
         if (b >= a.B) continue;
-        float x;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        float q = 0.f;
+        const float* xr = a.X32 + (size_t)b * a.xs + c;
+        for (int f = 0; f < a.nf; ++f) {
+            const float4 e = *reinterpret_cast<const float4*>(xr + (size_t)f * a.Dp);
+            s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+            q += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+        }
+        *reinterpret_cast<float4*>(a.S + (size_t)b * a.Dp + c) = s;
+        if (a.use_fm) {
+            atomicAdd(&sq[r], q);
+            atomicAdd(&sfm[r], s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w);
+        }
+    }
+    // linear terms: server rows (from X32) + cached rows + dense-linear
+    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc + 1); i += blockDim.x) {
+        const int per = a.ns + a.nc + 1;
+        const int r = i / per, j = i % per, b = b0 + r;
+        if (b >= a.B) continue;
+        float x = 0.f;
         if (j < a.ns) x = a.X32[(size_t)b * a.xs + a.lin0 + j];
-        else {
+        else if (j < a.ns + a.nc) {
             long long id = a.ids[(size_t)b * a.ncols + a.cache_col[j - a.ns]];
             x = a.cache_lin[a.cache_off[j - a.ns] + id];
+        } else {
+            for (int k = 0; k < a.nd; ++k) x += a.dense[(size_t)b * a.nd + k] * a.wd[k];
         }
         atomicAdd(&sl[r], x);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * a.Dp; i += blockDim.x) {
-        const int r = i / a.Dp, b = b0 + r;
-        if (b < a.B) a.S[(size_t)b * a.Dp + (i % a.Dp)] = sS[i];
-    }
     if (threadIdx.x < 32 && b0 + threadIdx.x < a.B) {
         const int r = threadIdx.x;
-        float fm = 0.f;
-        if (a.use_fm) {
-            for (int d = 0; d < a.Dp; ++d) fm += sS[r * a.Dp + d] * sS[r * a.Dp + d];
-            fm = 0.5f * (fm - sq[r]);
-        }
-        a.base[b0 + r] = sl[r] + fm + a.bias[0];
+        a.base[b0 + r] = sl[r] + (a.use_fm ? 0.5f * (sfm[r] - sq[r]) : 0.f) + a.bias[0];
     }
 }
 
@@ -356,8 +356,8 @@ const char* exb_dense_last_error() { return g_dense_err.c_str(); }
 
 int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
     PrepArgs a = *reinterpret_cast<const PrepArgs*>(args);
-    size_t smem = (32 * (size_t)Dp + 64) * 4;
-    exb_prep_kernel<<<(B + 31) / 32, 256, smem, (cudaStream_t)stream>>>(a);
+    (void)Dp;
+    exb_prep_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;

@@ -240,11 +240,12 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     for (int j = 0; j < 32; j += 4) {
                         float x[4];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int n = n0 + j + t;
-                            x[t] = __uint_as_float(v[j + t]);
-                            if (n < E.fm_cols)
-                                x[t] += dl * (E.S[(size_t)row * E.D + (n % E.D)] - E.emb[(size_t)row * E.ldemb + n]);
+                        for (int t = 0; t < 4; ++t) x[t] = __uint_as_float(v[j + t]);
+                        if (n0 + j + 3 < E.fm_cols) {   // fm_cols and D are multiples of 4
+                            const float4 s4 = *reinterpret_cast<const float4*>(E.S + (size_t)row * E.D + ((n0 + j) % E.D));
+                            const float4 e4 = *reinterpret_cast<const float4*>(E.emb + (size_t)row * E.ldemb + n0 + j);
+                            x[0] += dl * (s4.x - e4.x); x[1] += dl * (s4.y - e4.y);
+                            x[2] += dl * (s4.z - e4.z); x[3] += dl * (s4.w - e4.w);
                         }
                         if (n0 + j + 3 < E.N) *reinterpret_cast<float4*>(out + j) = make_float4(x[0], x[1], x[2], x[3]);
                         else

@@ -259,9 +259,13 @@ class FusedCTR:
             _ck(lib.exb_adagrad_flat(self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr(), self.n_theta,
                                      self.lr, self.eps, st), "adagrad")
             self.refresh_weights()
-        return self.loss
+        return self.loss.view(())
 
-    own_kernels_per_step = 15
+    def kernels_per_step(self):
+        """launches of our own kernels in one training step"""
+        L = len(self.hidden)
+        n = 1 + 1 + L + 1 + L + L + (1 if self.nc else 0) + 1 + 1 + L   # pull prep fwd head dX dW cache push adagrad refresh
+        return n + (5 if self._ar is not None else 0)
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)
     def reference(self, ids, dense, labels):
