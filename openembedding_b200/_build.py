@@ -45,7 +45,7 @@ def _hash(files, flags):
     h = hashlib.sha256()
     h.update(" ".join(flags).encode())
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, _HERE).encode())   # location independent: the tree is copied to the GPU box
         with open(f, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -75,7 +75,33 @@ def cuda_lib_path():
     return os.path.join(_LIB, "libexb_cuda.so")
 
 
+class _BuildLock:
+    """inter-process lock: torchrun ranks must not compile the same library concurrently"""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(_LIB, exist_ok=True)
+        self.fh = open(os.path.join(_LIB, ".build.lock"), "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+
+
 def build_core(force=False, verbose=False):
+    with _BuildLock():
+        return _build_core(force, verbose)
+
+
+def build_cuda(force=False, verbose=False):
+    with _BuildLock():
+        return _build_cuda(force, verbose)
+
+
+def _build_core(force=False, verbose=False):
     os.makedirs(_LIB, exist_ok=True)
     srcs = _sources("core", (".cpp",))
     deps = srcs + _sources("core", (".h",))
@@ -95,7 +121,7 @@ def build_core(force=False, verbose=False):
     return lib
 
 
-def build_cuda(force=False, verbose=False):
+def _build_cuda(force=False, verbose=False):
     os.makedirs(_OBJ, exist_ok=True)
     srcs = _sources("cuda", (".cu",))
     deps = srcs + _sources("cuda", (".cuh", ".h")) + _sources("core", (".h",))
