@@ -117,7 +117,7 @@ class Variable:
     """
 
     def __init__(self, initializer=None, trainable=None, name=None, dtype=None, shape=None, num_shards=None,
-                 sparse_as_dense=False, graph_var=None):
+                 sparse_as_dense=False, graph_var=None, host_tier_rows=None):
         if not num_shards:
             num_shards = -1
         if shape is not None:
@@ -162,8 +162,15 @@ class Variable:
         self._initialized = True
         self.graph_var = graph_var
         self.storage = ctx.create_storage(num_shards)
-        self.variable = ctx.create_variable(self.storage, shape[0], embedding_dim, dtype_name)
+        tiered = host_tier_rows is not None or bool(ctx.env["server"]["host_tier_root_path"]) \
+            or bool(ctx.env["server"]["pmem_pool_root_path"])
+        self.variable = ctx.create_variable(self.storage, shape[0], embedding_dim, dtype_name, force_hash=tiered,
+                                            capacity=(2 * host_tier_rows) if host_tier_rows else None)
         ctx.set_initializer(self.variable, initializer)
+        self.tier = None
+        if tiered:
+            from .host_tier import make_tiered
+            self.tier = make_tiered(ctx, self.variable, host_tier_rows)
         self.model_uuid = ctx.model_uuid
         self.optimizer_set = False
         self._prefetched = []
@@ -186,12 +193,16 @@ class Variable:
     def _pull(self, indices):
         ctx = get_context()
         flat = indices.reshape(-1)
+        if self.tier is not None:
+            self.tier.prefetch(flat)          # promote missing rows from the host store into HBM
         rows = ctx.backend.pull(self.variable, flat)
         return rows.reshape(tuple(indices.shape) + tuple(self._shape[1:])).to(self._tdtype)
 
     def _push(self, indices, grads):
         ctx = get_context()
         ctx.backend.push(self.variable, indices.reshape(-1), grads.reshape(-1, self.variable.dim))
+        if self.tier is not None:
+            self.tier.mark_updated(indices)
 
     def prefetch(self, indices, steps=None):
         """Stage the ids of a future batch on the device ahead of time.
@@ -238,6 +249,8 @@ class Variable:
         if self.sparse_as_dense:
             raise ValueError("no need update weights for sparse as dense.")
         get_context().backend.update([self.variable])
+        if self.tier is not None:
+            self.tier.next_work()
 
     def _finalize(self):
         self._initialized = False
@@ -268,7 +281,7 @@ class Embedding(nn.Module):
 
     def __init__(self, input_dim, output_dim, embeddings_initializer="uniform", embeddings_regularizer=None,
                  activity_regularizer=None, embeddings_constraint=None, mask_zero=False, input_length=None,
-                 num_shards=None, sparse_as_dense=False, explicit=True, dtype=None, name=None):
+                 num_shards=None, sparse_as_dense=False, explicit=True, dtype=None, name=None, host_tier_rows=None):
         super().__init__()
         if input_dim is None:
             input_dim = -1
@@ -303,7 +316,7 @@ class Embedding(nn.Module):
             self.embeddings = nn.Parameter(torch.zeros((1, self.output_dim), dtype=dtype, device=ctx.device))
             self.variable = Variable(initializer=dict(self.server_initializer), dtype=dtype,
                                      shape=(self.input_dim, self.output_dim), num_shards=num_shards,
-                                     graph_var=self.embeddings)
+                                     graph_var=self.embeddings, host_tier_rows=host_tier_rows)
         self.built = True
 
     def forward(self, inputs):
@@ -390,6 +403,9 @@ def _DistributedOptimizer(T):
                         p.grad = None          # the dummy [1, dim] parameter is never updated locally
             if tracked:
                 ctx.backend.update([v.variable for v in tracked])
+                for v in tracked:
+                    if v.tier is not None:
+                        v.tier.next_work()
             ctx.model_version += 1
             try:
                 return super().step(closure)

@@ -259,7 +259,8 @@ class CudaBackend:
     def create_variable(self, meta):
         if meta.dtype != "float32":
             raise ValueError("the CUDA engine stores float32 tables (use flags.device='cpu' for float64)")
-        t = self.engine.add_table(meta.dim, meta.vocab, meta.is_hash, capacity=self.hash_reserve,
+        t = self.engine.add_table(meta.dim, meta.vocab, meta.is_hash,
+                                  capacity=getattr(meta, "capacity", None) or self.hash_reserve,
                                   shard_num=meta.shard_num, shard_base=meta.shard_base)
         meta.handle = t
         meta.allocated = False

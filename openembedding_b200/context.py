@@ -85,10 +85,12 @@ class Context:
         self.storages.append(st)
         return st
 
-    def create_variable(self, storage, vocabulary_size, embedding_dim, dtype="float32"):
-        is_hash = vocabulary_size >= HASH_KEY_RANGE
+    def create_variable(self, storage, vocabulary_size, embedding_dim, dtype="float32", force_hash=False,
+                        capacity=None):
+        is_hash = vocabulary_size >= HASH_KEY_RANGE or force_hash
         meta = VarMeta(len(self.variables), storage.storage_id, int(vocabulary_size), int(embedding_dim),
                        dtype, is_hash, storage.shard_num, storage.shard_base)
+        meta.capacity = capacity
         self.backend.create_variable(meta)
         self.backend.set_initializer(meta, meta.initializer)
         storage.variables.append(meta)

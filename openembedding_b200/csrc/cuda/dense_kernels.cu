@@ -33,61 +33,74 @@ struct PrepArgs {
     int B, K0p, Dp, nf, ns, lin0, use_fm;   // lin0 = first column of the server linear terms in X32
 };
 
-// one CTA per 32 batch rows.
-//  phase A: thread t owns column (chunk*256 + t) of those 32 rows: gathers cached rows / dense
-//           features / the ones column, writes A0 (row major) and A0T (batch major, 64-byte runs)
-//  phase B: FM field sums with float4 loads (one thread per (row, 4 dims)), linear terms
-__global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
-    __shared__ float sq[32], sfm[32], sl[32];
+// prep A: grid (B/32, ceil(K0p/256)); thread t owns ONE column of 32 batch rows: gathers cached
+//         rows / dense features / the ones column, writes A0 (row major) and A0T (batch major,
+//         64-byte runs). 7x more CTAs than a per-row-block loop: the kernel is latency bound.
+__global__ void __launch_bounds__(256) exb_prep_a_kernel(PrepArgs a) {
     const int b0 = blockIdx.x * 32;
-    if (threadIdx.x < 32) { sq[threadIdx.x] = 0.f; sfm[threadIdx.x] = 0.f; sl[threadIdx.x] = 0.f; }
+    const int col = blockIdx.y * 256 + threadIdx.x;
+    if (col >= a.K0p) return;
     const int emb_cols = a.nf * a.Dp, srv_cols = a.ns * a.Dp;
-    for (int col = threadIdx.x; col < a.K0p; col += blockDim.x) {
-        float v[32];
-        const bool is_emb = col < emb_cols;
-        const int d = is_emb ? col % a.Dp : 0;
-        int cj = -1;
-        if (is_emb && col >= srv_cols) cj = (col - srv_cols) / a.Dp;
+    float v[32];
+    const bool is_emb = col < emb_cols;
+    const int d = is_emb ? col % a.Dp : 0;
+    int cj = -1;
+    if (is_emb && col >= srv_cols) cj = (col - srv_cols) / a.Dp;
+    long long coff = 0;
+    int ccol = 0;
+    if (cj >= 0) { coff = a.cache_off[cj]; ccol = a.cache_col[cj]; }
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const int b = b0 + r;
-            float x = 0.f;
-            if (b < a.B) {
-                if (col < srv_cols) x = a.X32[(size_t)b * a.xs + col];
-                else if (is_emb) {
-                    long long id = a.ids[(size_t)b * a.ncols + a.cache_col[cj]];
-                    x = a.cache_emb[(size_t)(a.cache_off[cj] + id) * a.Dp + d];
-                    a.X32[(size_t)b * a.xs + col] = x;
-                } else if (col < emb_cols + a.nd) x = a.dense[(size_t)b * a.nd + (col - emb_cols)];
-                else if (col == a.K0p - 1) x = 1.f;
-            }
-            v[r] = x;
+    for (int r = 0; r < 32; ++r) {
+        const int b = b0 + r;
+        float x = 0.f;
+        if (b < a.B) {
+            if (col < srv_cols) x = a.X32[(size_t)b * a.xs + col];
+            else if (is_emb) {
+                const long long id = a.ids[(size_t)b * a.ncols + ccol];
+                x = a.cache_emb[(size_t)(coff + id) * a.Dp + d];
+            } else if (col < emb_cols + a.nd) x = a.dense[(size_t)b * a.nd + (col - emb_cols)];
+            else if (col == a.K0p - 1) x = 1.f;
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
-            if (b0 + r < a.B) a.A0[(size_t)(b0 + r) * a.K0p + col] = h;
-            const uint16_t u = *reinterpret_cast<const uint16_t*>(&h);
-            if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
-        }
-        if (b0 + 31 < a.B) {
-            uint4* tp = reinterpret_cast<uint4*>(a.A0T + (size_t)col * a.B + b0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        } else {
-            for (int r = 0; r < 32 && b0 + r < a.B; ++r)
-                a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
-        }
+        v[r] = x;
     }
-    __syncthreads();   // cached columns of X32 written above are read below (same CTA)
+    if (cj >= 0) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            if (b0 + r < a.B) a.X32[(size_t)(b0 + r) * a.xs + col] = v[r];
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
+        if (b0 + r < a.B) a.A0[(size_t)(b0 + r) * a.K0p + col] = h;
+        const uint16_t u = *reinterpret_cast<const uint16_t*>(&h);
+        if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
+    }
+    if (b0 + 31 < a.B) {
+        uint4* tp = reinterpret_cast<uint4*>(a.A0T + (size_t)col * a.B + b0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    } else {
+        for (int r = 0; r < 32 && b0 + r < a.B; ++r)
+            a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
+    }
+}
+
+// prep B: one CTA per 8 batch rows: FM field sums with float4 loads (X32 is complete after
+//         prep A), linear terms, per-sample base logit
+__global__ void __launch_bounds__(256) exb_prep_b_kernel(PrepArgs a) {
+    __shared__ float sq[8], sfm[8], sl[8];
+    const int b0 = blockIdx.x * 8;
+    if (threadIdx.x < 8) { sq[threadIdx.x] = 0.f; sfm[threadIdx.x] = 0.f; sl[threadIdx.x] = 0.f; }
+    __syncthreads();
     const int q4 = a.Dp / 4;
-    for (int i = threadIdx.x; i < 32 * q4; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 8 * q4; i += blockDim.x) {
         const int r = i / q4, c = (i % q4) * 4, b = b0 + r;
         if (b >= a.B) continue;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         float q = 0.f;
         const float* xr = a.X32 + (size_t)b * a.xs + c;
+#pragma unroll 13
         for (int f = 0; f < a.nf; ++f) {
             const float4 e = *reinterpret_cast<const float4*>(xr + (size_t)f * a.Dp);
             s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
@@ -99,9 +112,8 @@ __global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
             atomicAdd(&sfm[r], s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w);
         }
     }
-    // linear terms: server rows (from X32) + cached rows + dense-linear
-    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc + 1); i += blockDim.x) {
-        const int per = a.ns + a.nc + 1;
+    const int per = a.ns + a.nc + 1;
+    for (int i = threadIdx.x; i < 8 * per; i += blockDim.x) {
         const int r = i / per, j = i % per, b = b0 + r;
         if (b >= a.B) continue;
         float x = 0.f;
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(256) exb_prep_kernel(PrepArgs a) {
         atomicAdd(&sl[r], x);
     }
     __syncthreads();
-    if (threadIdx.x < 32 && b0 + threadIdx.x < a.B) {
+    if (threadIdx.x < 8 && b0 + threadIdx.x < a.B) {
         const int r = threadIdx.x;
         a.base[b0 + r] = sl[r] + (a.use_fm ? 0.5f * (sfm[r] - sq[r]) : 0.f) + a.bias[0];
     }
@@ -136,91 +148,91 @@ struct HeadArgs {
     float grad_scale;                             // 1/B (mean loss)
 };
 
-__global__ void __launch_bounds__(256) exb_head_kernel(HeadArgs a) {
-    __shared__ float s_dl[32];
-    __shared__ float s_loss[8];
-    const int b0 = blockIdx.x * 32;
+// head A: one warp per batch row: logit, loss, dlogit; linear-term gradients of that row
+__global__ void __launch_bounds__(256) exb_head_a_kernel(HeadArgs a) {
+    __shared__ float s_loss[8], s_dl[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float lsum = 0.f;
-    for (int r = warp; r < 32; r += 8) {          // 4 rows per warp
-        const int b = b0 + r;
-        float z = 0.f;
-        if (b < a.B) {
-            const __nv_bfloat16* h = a.H + (size_t)b * a.Hp;
-            for (int n = lane; n < a.Hp; n += 32) z += __bfloat162float(h[n]) * a.wout[n];
-        }
-        for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-        if (lane == 0) {
-            float dl = 0.f;
-            if (b < a.B) {
-                z += a.base[b];
-                const float y = a.labels[b];
-                // numerically stable BCE with logits
-                const float l = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
-                const float p = 1.f / (1.f + expf(-z));
-                dl = (p - y) * a.grad_scale;
-                a.dlogit[b] = dl;
-                lsum += l * a.grad_scale;
-            }
-            s_dl[r] = dl;
+    const int b = blockIdx.x * 8 + warp;
+    float z = 0.f, dl = 0.f, l = 0.f;
+    if (b < a.B) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(a.H + (size_t)b * a.Hp);
+        const float2* w2 = reinterpret_cast<const float2*>(a.wout);
+        for (int n = lane; n < a.Hp / 2; n += 32) {
+            const float2 hv = __bfloat1622float2(h2[n]);
+            const float2 wv = w2[n];
+            z += hv.x * wv.x + hv.y * wv.y;
         }
     }
-    if (lane == 0) s_loss[warp] = lsum;
+    for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (b < a.B) {
+        z += a.base[b];
+        const float y = a.labels[b];
+        l = (fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)))) * a.grad_scale;   // stable BCE with logits
+        dl = (1.f / (1.f + expf(-z)) - y) * a.grad_scale;
+        if (lane == 0) a.dlogit[b] = dl;
+        // linear-term gradients: server rows -> G32, cached rows -> dense grad
+        for (int j = lane; j < a.ns + a.nc; j += 32) {
+            if (j < a.ns) a.G32[(size_t)b * a.xs + a.lin0 + j] = dl;
+            else {
+                long long id = a.ids[(size_t)b * a.ncols + a.cache_col[j - a.ns]];
+                atomicAdd(&a.g_cache_lin[a.cache_off[j - a.ns] + id], dl);
+            }
+        }
+    }
+    if (lane == 0) { s_loss[warp] = l; s_dl[warp] = dl; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += s_loss[i];
+        float t = 0.f, gb = 0.f;
+        for (int i = 0; i < 8; ++i) { t += s_loss[i]; gb += s_dl[i]; }
         atomicAdd(a.loss, t);
-        float gb = 0.f;
-        for (int r = 0; r < 32; ++r) gb += s_dl[r];
         atomicAdd(a.g_bias, gb);
     }
-    // dZ = dl * wout * relu'(H), both layouts; g_wout
-    for (int n = threadIdx.x; n < a.Hp; n += blockDim.x) {
-        const float w = a.wout[n];
-        float gw = 0.f;
-        uint32_t pk[16];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const int b = b0 + r;
-            float h = 0.f, dz = 0.f;
-            if (b < a.B) {
-                h = __bfloat162float(a.H[(size_t)b * a.Hp + n]);
-                gw += s_dl[r] * h;
-                if (h > 0.f && n != a.ones_col) dz = s_dl[r] * w;
-                a.dZ[(size_t)b * a.Hp + n] = __float2bfloat16_rn(dz);
-            }
-            const __nv_bfloat16 hb = __float2bfloat16_rn(dz);
-            const uint16_t u = *reinterpret_cast<const uint16_t*>(&hb);
-            if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
-        }
-        if (b0 + 31 < a.B) {
-            uint4* tp = reinterpret_cast<uint4*>(a.dZT + (size_t)n * a.B + b0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        } else {
-            for (int r = 0; r < 32 && b0 + r < a.B; ++r) {
-                const uint16_t u = (pk[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
-                a.dZT[(size_t)n * a.B + b0 + r] = *reinterpret_cast<const __nv_bfloat16*>(&u);
-            }
-        }
-        atomicAdd(&a.g_wout[n], gw);
-    }
-    // linear-term gradients: server rows -> G32, cached rows -> dense grad, dense-linear weights
-    for (int i = threadIdx.x; i < 32 * (a.ns + a.nc); i += blockDim.x) {
-        const int r = i / (a.ns + a.nc), j = i % (a.ns + a.nc), b = b0 + r;
-        if (b >= a.B) continue;
-        if (j < a.ns) a.G32[(size_t)b * a.xs + a.lin0 + j] = s_dl[r];
-        else {
-            long long id = a.ids[(size_t)b * a.ncols + a.cache_col[j - a.ns]];
-            atomicAdd(&a.g_cache_lin[a.cache_off[j - a.ns] + id], s_dl[r]);
-        }
-    }
-    for (int j = threadIdx.x; j < a.nd; j += blockDim.x) {
+    if ((int)threadIdx.x < a.nd) {     // dense-linear weight gradient, reduced over the CTA's 8 rows
         float g = 0.f;
-        for (int r = 0; r < 32 && b0 + r < a.B; ++r) g += s_dl[r] * a.dense[(size_t)(b0 + r) * a.nd + j];
-        atomicAdd(&a.g_wd[j], g);
+        for (int r = 0; r < 8; ++r) {
+            const int bb = blockIdx.x * 8 + r;
+            if (bb < a.B) g += s_dl[r] * a.dense[(size_t)bb * a.nd + threadIdx.x];
+        }
+        atomicAdd(&a.g_wd[threadIdx.x], g);
     }
+}
+
+// head B: grid (B/32, ceil(Hp/256)); thread = one column of 32 rows:
+//         dZ = dl * wout * relu'(H) in both layouts, g_wout
+__global__ void __launch_bounds__(256) exb_head_b_kernel(HeadArgs a) {
+    __shared__ float s_dl[32];
+    const int b0 = blockIdx.x * 32;
+    if (threadIdx.x < 32) s_dl[threadIdx.x] = (b0 + threadIdx.x < a.B) ? a.dlogit[b0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    const int n = blockIdx.y * 256 + threadIdx.x;
+    if (n >= a.Hp) return;
+    const float w = a.wout[n];
+    float gw = 0.f;
+    float hv[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) hv[r] = (b0 + r < a.B) ? __bfloat162float(a.H[(size_t)(b0 + r) * a.Hp + n]) : 0.f;
+    uint32_t pk[16];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        float dz = 0.f;
+        gw += s_dl[r] * hv[r];
+        if (hv[r] > 0.f && n != a.ones_col) dz = s_dl[r] * w;
+        const __nv_bfloat16 hb = __float2bfloat16_rn(dz);
+        if (b0 + r < a.B) a.dZ[(size_t)(b0 + r) * a.Hp + n] = hb;
+        const uint16_t u = *reinterpret_cast<const uint16_t*>(&hb);
+        if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
+    }
+    if (b0 + 31 < a.B) {
+        uint4* tp = reinterpret_cast<uint4*>(a.dZT + (size_t)n * a.B + b0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    } else {
+        for (int r = 0; r < 32 && b0 + r < a.B; ++r) {
+            const uint16_t u = (pk[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+            a.dZT[(size_t)n * a.B + b0 + r] = *reinterpret_cast<const __nv_bfloat16*>(&u);
+        }
+    }
+    atomicAdd(&a.g_wout[n], gw);
 }
 
 // scatter-add the gradient rows of the cached (replicated) embedding tables
@@ -357,7 +369,9 @@ const char* exb_dense_last_error() { return g_dense_err.c_str(); }
 int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
     PrepArgs a = *reinterpret_cast<const PrepArgs*>(args);
     (void)Dp;
-    exb_prep_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a);
+    dim3 ga((B + 31) / 32, (a.K0p + 255) / 256);
+    exb_prep_a_kernel<<<ga, 256, 0, (cudaStream_t)stream>>>(a);
+    exb_prep_b_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
@@ -365,7 +379,9 @@ int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
 int exb_prep_args_size() { return (int)sizeof(PrepArgs); }
 int exb_head(const void* args, int B, uint64_t stream) {
     HeadArgs a = *reinterpret_cast<const HeadArgs*>(args);
-    exb_head_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a);
+    exb_head_a_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
+    dim3 gb((B + 31) / 32, (a.Hp + 255) / 256);
+    exb_head_b_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;

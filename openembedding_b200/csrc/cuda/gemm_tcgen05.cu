@@ -3,7 +3,7 @@
 //   D[M,N] (+)= A[M,K] * B[N,K]^T      A, B bf16 K-major, fp32 accumulation in TMEM
 //
 // One 128x64 output tile per CTA (optionally one K-split of it), warp specialised:
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 6-stage smem ring
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring
 //   warp 1      MMA issuer     one elected thread, tcgen05.mma.cta_group::1.kind::f16,
 //                              128x64x16 per instruction, accumulator = 64 TMEM columns;
 //                              tcgen05.commit frees the smem stage / signals the epilogue
@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 64, STAGES = 6;
+constexpr int BM = 128, BN = 64, BK = 64, STAGES = 4;   // 96 KB of stages: two CTAs per SM
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int NUM_THREADS = 192;
 
@@ -98,7 +98,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         GemmEpi E, int num_k_blocks, int k_blocks_per_split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -163,11 +163,16 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        // TMEM hands every thread one ROW (32 consecutive columns). Stores/loads in that layout
+        // touch 32 different lines per instruction, so each warp transposes its 32x32 block
+        // through shared memory (the pipeline stages are free once tmem_full fired) and does
+        // the fused math + global traffic with lanes along the COLUMNS (128-byte rows).
         const int q = warp & 3;
-        const int row = m_blk * BM + q * 32 + lane;
+        const int row0 = m_blk * BM + q * 32;
         bool ok = true;
         if (nkb > 0) ok = mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -176,84 +181,57 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            const int n0 = n_blk * BN + c0;
-            if (E.mode == EPI_FWD || E.mode == EPI_DX) {
-                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(E.out);
-                uint32_t packed[16];
-                uint4 mk[4];
-                if (E.mode == EPI_DX && row < E.M) {
-                    const uint4* mp = reinterpret_cast<const uint4*>(E.mask + (size_t)row * E.ldmask + n0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) mk[j] = mp[j];
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int n = n_blk * BN + c0 + lane;
+            // issue every global read of the block first (32 independent loads per lane in flight)
+            float aux[32];
+            if (E.mode == EPI_DX) {
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr)
+                    aux[rr] = (row0 + rr < E.M) ? __bfloat162float(E.mask[(size_t)(row0 + rr) * E.ldmask + n]) : 0.f;
+            } else if (E.mode == EPI_DX_FM) {
+                const bool fm = n < E.fm_cols;
+                const int dcol = n % E.D;
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = row0 + rr;
+                    aux[rr] = (fm && row < E.M) ? (E.S[(size_t)row * E.D + dcol] - E.emb[(size_t)row * E.ldemb + n]) : 0.f;
                 }
-                const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(mk);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    const int n = n0 + j;
+                for (int rr = 0; rr < 32; ++rr)
+                    if (fm && row0 + rr < E.M) aux[rr] *= E.dlogit[row0 + rr];
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+                const int row = row0 + rr;
+                float x = stg[rr * 33 + lane];
+                if (row < E.M) {
                     if (E.mode == EPI_FWD) {
                         if (E.relu) x = fmaxf(x, 0.f);
                         if (n == E.ones_col) x = 1.f;
-                    } else {
-                        if (!(__bfloat162float(mh[j]) > 0.f) || n == E.ones_col) x = 0.f;
-                    }
-                    if (n >= E.N) x = 0.f;
-                    v[j] = __float_as_uint(x);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    packed[j] = *reinterpret_cast<uint32_t*>(&p);
-                }
-                if (row < E.M) {
-                    uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * E.ldo + n0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    if (E.outT) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[j]));
-                            E.outT[(size_t)(n0 + j) * E.ldoT + row] = h;   // lanes = consecutive rows: coalesced
-                        }
+                        if (n >= E.N) x = 0.f;
+                        reinterpret_cast<__nv_bfloat16*>(E.out)[(size_t)row * E.ldo + n] = __float2bfloat16_rn(x);
+                    } else if (E.mode == EPI_DX) {
+                        if (!(aux[rr] > 0.f) || n == E.ones_col || n >= E.N) x = 0.f;
+                        reinterpret_cast<__nv_bfloat16*>(E.out)[(size_t)row * E.ldo + n] = __float2bfloat16_rn(x);
+                    } else if (E.mode == EPI_DW) {
+                        if (n < E.N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(E.out) + (size_t)row * E.ldo + n), "f"(x) : "memory");
+                    } else {   // EPI_DX_FM
+                        x += aux[rr];
+                        if (n < E.N) reinterpret_cast<float*>(E.out)[(size_t)row * E.ldo + n] = x;
                     }
                 }
-            } else if (E.mode == EPI_DW) {
-                if (row < E.M) {
-                    float* out = reinterpret_cast<float*>(E.out) + (size_t)row * E.ldo + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (n0 + j + 3 < E.N) {
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j),
-                                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
-                        } else {
-                            for (int t = 0; t < 4; ++t)
-                                if (n0 + j + t < E.N) atomicAdd(out + j + t, __uint_as_float(v[j + t]));
-                        }
-                    }
-                }
-            } else {   // EPI_DX_FM
-                if (row < E.M) {
-                    float* out = reinterpret_cast<float*>(E.out) + (size_t)row * E.ldo + n0;
-                    const float dl = E.dlogit ? E.dlogit[row] : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float x[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) x[t] = __uint_as_float(v[j + t]);
-                        if (n0 + j + 3 < E.fm_cols) {   // fm_cols and D are multiples of 4
-                            const float4 s4 = *reinterpret_cast<const float4*>(E.S + (size_t)row * E.D + ((n0 + j) % E.D));
-                            const float4 e4 = *reinterpret_cast<const float4*>(E.emb + (size_t)row * E.ldemb + n0 + j);
-                            x[0] += dl * (s4.x - e4.x); x[1] += dl * (s4.y - e4.y);
-                            x[2] += dl * (s4.z - e4.z); x[3] += dl * (s4.w - e4.w);
-                        }
-                        if (n0 + j + 3 < E.N) *reinterpret_cast<float4*>(out + j) = make_float4(x[0], x[1], x[2], x[3]);
-                        else
-                            for (int t = 0; t < 4; ++t)
-                                if (n0 + j + t < E.N) out[j + t] = x[t];
-                    }
-                }
+                if (E.outT) stg[rr * 33 + lane] = x;
             }
+            __syncwarp();
+            if (E.outT && row0 + lane < E.M) {   // lanes = consecutive rows: coalesced transposed copy
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    E.outT[(size_t)(n_blk * BN + c0 + j) * E.ldoT + row0 + lane] = __float2bfloat16_rn(stg[lane * 33 + j]);
+            }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }

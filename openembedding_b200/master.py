@@ -1,22 +1,26 @@
-"""Control plane: ``Master`` (rendezvous KV tree) and ``Server`` (standalone shard host).
+"""Control plane: ``Master`` (rendezvous KV tree), ``MasterClient`` and the ``Server`` shim.
 
 Reference: the TCP master is a single-thread poll() KV tree with ephemeral nodes and
-watchers (pico-core rpc/Master.cpp:139-304) used for rank generation, barriers, locks
-and the model registry; ``Server`` joins a job as a dedicated PS process
+watchers (pico-core rpc/Master.cpp:139-304); ``MasterClient`` offers tree_node_*, barrier,
+acquire/release_lock, generate_id and the rpc/node/model registries
+(rpc/MasterClient.h:56-160); ``Server`` joins a job as a dedicated PS process
 (openembedding/entry/server.cc:25-60, py_api.cc:164-215).
 
-B200 design: inside one NVSwitch box every rank hosts its own shards in HBM, so the
-data plane needs no server process. The control plane keeps the same verbs on top of a
-``torch.distributed.TCPStore`` (tree paths are store keys): ``Master`` owns the store
-server and hands out ``endpoint``; ``MasterClient`` provides tree_node_*/barrier/
-acquire_lock/generate_id; ``Server`` is the out-of-job serving host (see
-``serving/``).
+B200 design: inside one NVSwitch box every rank hosts its own shards in HBM, so training
+needs no server process and no data-plane RPC. The control plane keeps the same verbs on top
+of a ``torch.distributed.TCPStore`` (the store server thread plays the master): tree paths
+are store keys, children are tracked in an append-only per-parent index, ephemeral nodes are
+heartbeat leases (a node whose lease is older than ``LEASE_S`` is dead -- the reference drops
+them on socket close, Master.cpp:203).
 """
 import datetime
 import socket
 import threading
 import time
 import uuid
+
+LEASE_S = 5.0
+_TOMB = "\x00deleted"
 
 
 def _free_port():
@@ -36,95 +40,137 @@ class Master:
         self.port = port or _free_port()
         self._store = TCPStore(self.ip, self.port, is_master=True, wait_for_workers=False,
                                timeout=datetime.timedelta(seconds=3600))
-        self._closed = False
 
     @property
     def endpoint(self):
         return "%s:%d" % (self.ip, self.port)
 
-    def client(self):
-        return MasterClient(self.endpoint, store=self._store)
+    def client(self, **kw):
+        return MasterClient(self.endpoint, **kw)
 
     def finalize(self):
-        self._closed = True
         self._store = None
 
     join = finalize
 
 
 class MasterClient:
-    """Tree/barrier/lock/id verbs of pico-core MasterClient (rpc/MasterClient.h:56-160)."""
+    """Tree / barrier / lock / id verbs (pico-core rpc/MasterClient.h:56-160)."""
 
-    def __init__(self, endpoint, root_path="/openembedding", store=None, timeout=3600):
+    def __init__(self, endpoint, root_path="/openembedding", timeout=3600):
         from torch.distributed import TCPStore
         ip, port = endpoint.rsplit(":", 1)
-        self.root = root_path.rstrip("/")
-        self._store = store or TCPStore(ip, int(port), is_master=False,
-                                        timeout=datetime.timedelta(seconds=timeout))
+        self.endpoint = endpoint
+        self.root = "/" + root_path.strip("/")
+        self._store = TCPStore(ip, int(port), is_master=False, timeout=datetime.timedelta(seconds=timeout))
         self._session = uuid.uuid4().hex
+        self._leases = {}
+        self._hb = None
+        self._stop = threading.Event()
 
-    def _k(self, path):
-        return self.root + "/" + path.strip("/")
+    # ---- key helpers
+    def _norm(self, path):
+        return "/" + path.strip("/") if path.strip("/") else ""
 
-    # -- tree
+    def _vk(self, path):
+        return "v:" + self.root + self._norm(path)
+
+    def _ik(self, path):
+        return "i:" + self.root + self._norm(path)
+
+    def _get(self, key):
+        if not self._store.check([key]):
+            return None
+        v = self._store.get(key).decode()
+        return None if v == _TOMB else v
+
+    def _index_child(self, path):
+        p = self._norm(path)
+        if not p:
+            return
+        parent, _, name = p.rpartition("/")
+        self._store.append(self._ik(parent), name + "\n")
+
+    # ---- tree
     def tree_node_add(self, path, value="", ephemeral=False):
-        key = self._k(path)
-        # compare_set with empty expected value creates the key only if it did not exist
-        got = self._store.compare_set(key, "", "v:" + value)
-        ok = got.decode() == "v:" + value
+        """create; False if the node already exists"""
+        key = self._vk(path)
+        cur = self._store.compare_set(key, "", value if value else " ").decode()
+        ok = cur == (value if value else " ")
+        if not ok and cur == _TOMB:
+            cur = self._store.compare_set(key, _TOMB, value if value else " ").decode()
+            ok = cur == (value if value else " ")
         if ok:
-            self._store.add(self._k("__children__/" + path.strip("/").rsplit("/", 1)[0] if "/" in path.strip("/") else "__children__/"), 1)
-            idx_key = self._k("__index__")
-            self._store.append(idx_key, key + "\n") if hasattr(self._store, "append") else None
+            self._index_child(path)
+            if ephemeral:
+                self._lease(path)
         return ok
 
     def tree_node_set(self, path, value):
-        self._store.set(self._k(path), "v:" + value)
-        if hasattr(self._store, "append"):
-            self._store.append(self._k("__index__"), self._k(path) + "\n")
+        existed = self._get(self._vk(path)) is not None
+        self._store.set(self._vk(path), value if value else " ")
+        if not existed:
+            self._index_child(path)
         return True
 
     def tree_node_get(self, path, default=None):
-        key = self._k(path)
-        if not self._store.check([key]):
+        v = self._get(self._vk(path))
+        if v is None or not self._alive(path):
             return default
-        v = self._store.get(key).decode()
-        if v == "v:\x00deleted":
-            return default
-        return v[2:] if v.startswith("v:") else v
+        return "" if v == " " else v
 
     def tree_node_del(self, path):
-        key = self._k(path)
-        if not self._store.check([key]):
+        if self._get(self._vk(path)) is None:
             return False
-        self._store.set(key, "v:\x00deleted")
+        self._store.set(self._vk(path), _TOMB)
+        self._leases.pop(self._norm(path), None)
         return True
 
     def tree_node_sub(self, path):
-        prefix = self._k(path).rstrip("/") + "/"
-        idx = self._k("__index__")
-        if not self._store.check([idx]):
+        """names of the live children of `path`"""
+        ik = self._ik(path)
+        if not self._store.check([ik]):
             return []
-        keys = sorted(set(k for k in self._store.get(idx).decode().split("\n") if k.startswith(prefix)))
-        out = []
-        for k in keys:
-            rest = k[len(prefix):]
-            if "/" in rest:
-                continue
-            v = self._store.get(k).decode()
-            if v != "v:\x00deleted":
-                out.append(rest)
-        return out
+        names = sorted(set(n for n in self._store.get(ik).decode().split("\n") if n))
+        base = self._norm(path)
+        return [n for n in names if self._get(self._vk(base + "/" + n)) is not None and self._alive(base + "/" + n)]
 
-    # -- ids / barriers / locks
+    # ---- ephemeral nodes = heartbeat leases
+    def _lk(self, path):
+        return "l:" + self.root + self._norm(path)
+
+    def _lease(self, path):
+        self._leases[self._norm(path)] = True
+        self._store.set(self._lk(path), repr(time.time()))
+        if self._hb is None:
+            self._hb = threading.Thread(target=self._beat, daemon=True)
+            self._hb.start()
+
+    def _beat(self):
+        while not self._stop.wait(LEASE_S / 3):
+            for p in list(self._leases):
+                try:
+                    self._store.set(self._lk(p), repr(time.time()))
+                except Exception:
+                    return
+
+    def _alive(self, path):
+        lk = self._lk(path)
+        if not self._store.check([lk]):
+            return True          # not ephemeral
+        return time.time() - float(self._store.get(lk).decode()) < LEASE_S
+
+    def close(self):
+        self._stop.set()
+
+    # ---- ids / barriers / locks
     def generate_id(self, name):
-        return int(self._store.add(self._k("__id__/" + name), 1)) - 1
+        return int(self._store.add("id:" + self.root + "/" + name, 1)) - 1
 
     def barrier(self, name, n, timeout=3600):
-        key = self._k("__barrier__/" + name)
+        key = "b:" + self.root + "/" + name
         arrived = int(self._store.add(key, 1))
-        generation = (arrived - 1) // n
-        target = (generation + 1) * n
+        target = ((arrived - 1) // n + 1) * n
         t0 = time.time()
         while int(self._store.add(key, 0)) < target:
             if time.time() - t0 > timeout:
@@ -132,40 +178,40 @@ class MasterClient:
             time.sleep(0.002)
 
     def acquire_lock(self, name, timeout=3600):
-        key = self._k("__lock__/" + name)
+        key = "k:" + self.root + "/" + name
         t0 = time.time()
         while True:
-            got = self._store.compare_set(key, "", self._session).decode()
-            if got == self._session:
-                return
-            if got == "free":
-                got = self._store.compare_set(key, "free", self._session).decode()
-                if got == self._session:
+            for expected in ("", "free"):
+                if self._store.compare_set(key, expected, self._session).decode() == self._session:
                     return
             if time.time() - t0 > timeout:
                 raise TimeoutError("master lock " + name)
             time.sleep(0.002)
 
     def release_lock(self, name):
-        self._store.set(self._k("__lock__/" + name), "free")
+        self._store.set("k:" + self.root + "/" + name, "free")
 
 
 class Server:
-    """Standalone shard host for serving (see ``serving.ServingNode``).
+    """Standalone shard host for serving (``serving.node.ServingNode`` in a thread).
 
-    Training on one box never needs it: ``flags.wait_num_servers == -1`` (each worker
-    hosts its shards in its own HBM) is the only training topology.
+    Training on one box never needs it: ``flags.wait_num_servers == -1`` (each worker hosts
+    its shards in its own HBM) is the only training topology.
     """
 
-    def __init__(self, master_endpoint="", bind_ip="127.0.0.1", config=""):
+    def __init__(self, master_endpoint="", bind_ip="127.0.0.1", config="", port=0):
         from .serving.node import ServingNode
-        self._node = ServingNode(master_endpoint=master_endpoint, bind_ip=bind_ip, config=config)
+        self._node = ServingNode(master_endpoint=master_endpoint, bind_ip=bind_ip, config=config, port=port)
         self._thread = threading.Thread(target=self._node.serve_forever, daemon=True)
         self._thread.start()
 
     @property
     def endpoint(self):
         return self._node.endpoint
+
+    @property
+    def node_id(self):
+        return self._node.node_id
 
     def exit(self):
         self._node.shutdown()

@@ -264,7 +264,7 @@ class FusedCTR:
     def kernels_per_step(self):
         """launches of our own kernels in one training step"""
         L = len(self.hidden)
-        n = 1 + 1 + L + 1 + L + L + (1 if self.nc else 0) + 1 + 1 + L   # pull prep fwd head dX dW cache push adagrad refresh
+        n = 1 + 2 + L + 2 + L + L + (1 if self.nc else 0) + 1 + 1 + L   # pull prep(2) fwd head(2) dX dW cache push adagrad refresh
         return n + (5 if self._ar is not None else 0)
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)

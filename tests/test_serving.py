@@ -1,0 +1,110 @@
+"""Serving stack: export -> controller create_model (replicas) -> read-only pulls -> node
+failure -> failover + restore. Reference analogues: c_api_test `model_mix`/`model_shard_num`
+(openembedding/entry/c_api_test.cpp:40-66) and c_api_ha_test (kill servers while pulling)."""
+import json
+import tempfile
+import time
+import urllib.request
+
+import pytest
+import torch
+
+
+def _export_model(d):
+    import openembedding_b200.torch as embed
+    from openembedding_b200.context import get_context
+    ctx = get_context()
+    emb = embed.Embedding(5000, 6, embeddings_initializer="uniform")
+    hemb = embed.Embedding(-1, 3, embeddings_initializer="normal")
+    opt = embed.distributed_optimizer(torch.optim.Adagrad(list(emb.parameters()) + list(hemb.parameters()), lr=0.1,
+                                                          initial_accumulator_value=0.1))
+    g = torch.Generator().manual_seed(0)
+    for _ in range(5):
+        x = torch.randint(0, 500, (64,), generator=g)
+        loss = (emb(x).sum(-1) + hemb(x * 7919).sum(-1)).pow(2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+    embed.save_server_model(None, d + "/model", include_optimizer=False)
+    ids = torch.arange(0, 600)
+    return ctx.model_sign(), emb(ids).detach().clone(), hemb(ids * 7919).detach().clone()
+
+
+def test_master_tree_barrier_lock():
+    from openembedding_b200.master import Master
+    m = Master()
+    a, b = m.client(), m.client()
+    assert a.tree_node_add("x/y", "1") and not b.tree_node_add("x/y", "2")
+    assert b.tree_node_get("x/y") == "1"
+    a.tree_node_set("x/z", "3")
+    assert sorted(b.tree_node_sub("x")) == ["y", "z"]
+    assert a.tree_node_del("x/y") and b.tree_node_get("x/y") is None and b.tree_node_sub("x") == ["z"]
+    assert a.tree_node_add("x/y", "again")
+    assert [a.generate_id("n"), b.generate_id("n"), a.generate_id("n")] == [0, 1, 2]
+    a.acquire_lock("L")
+    with pytest.raises(TimeoutError):
+        b.acquire_lock("L", timeout=0.1)
+    a.release_lock("L")
+    b.acquire_lock("L", timeout=1)
+    import threading
+    done = []
+    ts = [threading.Thread(target=lambda c=c: (c.barrier("B", 2), done.append(1))) for c in (a, b)]
+    [t.start() for t in ts]
+    [t.join(5) for t in ts]
+    assert done == [1, 1]
+
+
+@pytest.mark.parametrize("shard_num,replicas", [(-1, 2), (7, 3), (1, 1)])
+def test_serving_replicas_failover_restore(cpu_context, shard_num, replicas):
+    import openembedding_b200 as oe
+    from openembedding_b200.serving.client import NoReplica, ServingClient
+    from openembedding_b200.serving.controller import ModelController, serve
+    d = tempfile.mkdtemp()
+    sign, want_e, want_h = _export_model(d)
+    master = oe.Master()
+    servers = [oe.Server(master_endpoint=master.endpoint) for _ in range(3)]
+    httpd, _ = serve(master.endpoint, port=0, bind_ip="127.0.0.1")
+    import threading
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    base = "http://127.0.0.1:%d" % httpd.server_address[1]
+    req = urllib.request.Request(base + "/models", method="POST", headers={"Content-Type": "application/json"},
+                                 data=json.dumps({"model_uri": d + "/model", "replica_num": replicas,
+                                                  "shard_num": shard_num}).encode())
+    got = json.loads(urllib.request.urlopen(req, timeout=60).read())
+    assert got["model_sign"] == sign
+    rec = json.loads(urllib.request.urlopen(base + "/models/" + sign).read())
+    assert rec["model_status"] == "NORMAL" and rec["replica_num"] == min(replicas, 3)
+    assert len(json.loads(urllib.request.urlopen(base + "/nodes").read())) == 3
+    cli = ServingClient(master.endpoint)
+    ids = torch.arange(0, 600)
+    ve, vh = cli.find_model_variable(sign, 0), cli.find_model_variable(sign, 1)
+    assert torch.allclose(ve.pull(ids), want_e) and torch.allclose(vh.pull(ids * 7919), want_h)
+    if replicas >= 2:
+        # kill one node: pulls keep working from the other replica
+        servers[0].exit()
+        time.sleep(0.2)
+        assert torch.allclose(ve.pull(ids, timeout=20), want_e)
+        # a fresh node restores the dead node's shards (peer streaming) and takes its place
+        fresh = oe.Server(master_endpoint=master.endpoint)
+        restored = ModelController(master.endpoint).restore_node(fresh.node_id, fresh.endpoint)
+        assert restored
+        deadline = time.time() + 20
+        while time.time() < deadline:
+            st = json.loads(urllib.request.urlopen("http://%s/models" % fresh.endpoint).read())
+            if st.get(sign, {}).get("status") == "NORMAL":
+                break
+            time.sleep(0.05)
+        servers[1].exit()        # now the ORIGINAL second replica dies too
+        time.sleep(0.2)
+        cli2 = ServingClient(master.endpoint)
+        assert torch.allclose(cli2.find_model_variable(sign, 0).pull(ids, timeout=20), want_e)
+        servers.append(fresh)
+    else:
+        servers[0].exit(); servers[1].exit(); servers[2].exit()
+        with pytest.raises(NoReplica):
+            ve.pull(ids, timeout=1.0)
+    urllib.request.urlopen(urllib.request.Request(base + "/models/" + sign, method="DELETE")).read()
+    for s in servers:
+        try:
+            s.exit()
+        except Exception:
+            pass
+    httpd.shutdown()
