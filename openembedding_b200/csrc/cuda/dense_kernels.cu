@@ -41,48 +41,53 @@ __global__ void __launch_bounds__(256) exb_prep_a_kernel(PrepArgs a) {
     const int col = blockIdx.y * 256 + threadIdx.x;
     if (col >= a.K0p) return;
     const int emb_cols = a.nf * a.Dp, srv_cols = a.ns * a.Dp;
+    const bool full = b0 + 31 < a.B;
     float v[32];
-    const bool is_emb = col < emb_cols;
-    const int d = is_emb ? col % a.Dp : 0;
-    int cj = -1;
-    if (is_emb && col >= srv_cols) cj = (col - srv_cols) / a.Dp;
-    long long coff = 0;
-    int ccol = 0;
-    if (cj >= 0) { coff = a.cache_off[cj]; ccol = a.cache_col[cj]; }
+    // every path below is a fully unrolled batch of 32 INDEPENDENT loads (v[] stays in registers)
+    if (col < srv_cols) {
+        const float* src = a.X32 + (size_t)b0 * a.xs + col;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const int b = b0 + r;
-        float x = 0.f;
-        if (b < a.B) {
-            if (col < srv_cols) x = a.X32[(size_t)b * a.xs + col];
-            else if (is_emb) {
-                const long long id = a.ids[(size_t)b * a.ncols + ccol];
-                x = a.cache_emb[(size_t)(coff + id) * a.Dp + d];
-            } else if (col < emb_cols + a.nd) x = a.dense[(size_t)b * a.nd + (col - emb_cols)];
-            else if (col == a.K0p - 1) x = 1.f;
-        }
-        v[r] = x;
-    }
-    if (cj >= 0) {
+        for (int r = 0; r < 32; ++r) v[r] = (full || b0 + r < a.B) ? src[(size_t)r * a.xs] : 0.f;
+    } else if (col < emb_cols) {
+        const int cj = (col - srv_cols) / a.Dp, d = col % a.Dp;
+        const long long coff = a.cache_off[cj];
+        const long long* idp = a.ids + (size_t)b0 * a.ncols + a.cache_col[cj];
+        long long id[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) id[r] = (full || b0 + r < a.B) ? idp[(size_t)r * a.ncols] : 0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = a.cache_emb[(size_t)(coff + id[r]) * a.Dp + d];
+        float* dst = a.X32 + (size_t)b0 * a.xs + col;
 #pragma unroll
         for (int r = 0; r < 32; ++r)
-            if (b0 + r < a.B) a.X32[(size_t)(b0 + r) * a.xs + col] = v[r];
+            if (full || b0 + r < a.B) dst[(size_t)r * a.xs] = v[r];
+    } else if (col < emb_cols + a.nd) {
+        const float* src = a.dense + (size_t)b0 * a.nd + (col - emb_cols);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = (full || b0 + r < a.B) ? src[(size_t)r * a.nd] : 0.f;
+    } else {
+        const float c = (col == a.K0p - 1) ? 1.f : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = c;
     }
     uint32_t pk[16];
+    __nv_bfloat16* a0 = a.A0 + (size_t)b0 * a.K0p + col;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
-        if (b0 + r < a.B) a.A0[(size_t)(b0 + r) * a.K0p + col] = h;
-        const uint16_t u = *reinterpret_cast<const uint16_t*>(&h);
-        if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
+    for (int r = 0; r < 32; r += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[r]), h1 = __float2bfloat16_rn(v[r + 1]);
+        if (full || b0 + r < a.B) a0[(size_t)r * a.K0p] = h0;
+        if (full || b0 + r + 1 < a.B) a0[(size_t)(r + 1) * a.K0p] = h1;
+        pk[r >> 1] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h0)) |
+                     ((uint32_t)(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
     }
-    if (b0 + 31 < a.B) {
+    if (full) {
         uint4* tp = reinterpret_cast<uint4*>(a.A0T + (size_t)col * a.B + b0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     } else {
-        for (int r = 0; r < 32 && b0 + r < a.B; ++r)
-            a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            if (b0 + r < a.B) a.A0T[(size_t)col * a.B + b0 + r] = __float2bfloat16_rn(v[r]);
     }
 }
 

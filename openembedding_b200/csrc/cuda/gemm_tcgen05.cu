@@ -29,8 +29,10 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 64, STAGES = 4;   // 96 KB of stages: two CTAs per SM
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+// BN = 64: 96 KB of stages, two CTAs per SM (small-N GEMMs); BN = 256: 192 KB, one CTA per SM,
+// 4x fewer re-reads of the A operand (the wide dX1 / dW1 GEMMs are L2-bandwidth bound at BN = 64)
 constexpr int NUM_THREADS = 192;
 
 enum EpiMode : int { EPI_FWD = 0, EPI_DX = 1, EPI_DW = 2, EPI_DX_FM = 3 };
@@ -98,9 +100,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, (BN <= 64 ? 2 : 1))
 exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         GemmEpi E, int num_k_blocks, int k_blocks_per_split) {
+    constexpr int B_BYTES = BN * BK * 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases; do not rely on the toolchain for it
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -272,7 +276,8 @@ bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols,
     return true;
 }
 
-constexpr size_t GEMM_SMEM = STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+template <int BN>
+constexpr size_t gemm_smem() { return STAGES * (A_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
 
 }  // namespace
 
@@ -289,6 +294,7 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     if (K % BK != 0 || lda % 8 != 0 || ldb % 8 != 0) { g_gemm_err = "gemm: K %% 64 / ld %% 8 violated"; return -1; }
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, (const void*)A, M, K, lda, BM)) return -1;
+    const int BN = (N >= 1024) ? 256 : 64;
     if (!make_map(&tmB, (const void*)B, N, K, ldb, BN)) return -1;
     GemmEpi E;
     E.mode = mode; E.relu = relu; E.ones_col = ones_col; E.fm_cols = fm_cols; E.M = M; E.N = N; E.D = D > 0 ? D : 1; E._pad = 0;
@@ -297,7 +303,8 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     E.dlogit = (const float*)dlogit; E.S = (const float*)S; E.emb = (const float*)emb; E.ldemb = ldemb;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
+        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<256>());
         attr_set = true;
     }
     const int nkb = K / BK;
@@ -306,7 +313,10 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    exb_gemm_tcgen05_kernel<<<grid, NUM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, E, nkb, per);
+    if (BN == 64)
+        exb_gemm_tcgen05_kernel<64><<<grid, NUM_THREADS, gemm_smem<64>(), (cudaStream_t)stream>>>(tmA, tmB, E, nkb, per);
+    else
+        exb_gemm_tcgen05_kernel<256><<<grid, NUM_THREADS, gemm_smem<256>(), (cudaStream_t)stream>>>(tmA, tmB, E, nkb, per);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(err); return -1; }
     return 0;

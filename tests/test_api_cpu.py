@@ -1,0 +1,130 @@
+"""Public API semantics on the CPU backend (mirrors the contract of openembedding/tensorflow/exb.py)."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+
+class _Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.big = torch.nn.Embedding(1000, 8)
+        self.small = torch.nn.Embedding(10, 4)
+        self.out = torch.nn.Linear(12, 1)
+
+    def forward(self, x, y):
+        return self.out(torch.cat([self.big(x), self.small(y)], -1)).squeeze(-1)
+
+
+def test_distributed_model_replaces_embeddings(cpu_context):
+    import openembedding_b200.torch as embed
+    m = embed.distributed_model(_Net(), sparse_as_dense_size=64)
+    assert isinstance(m.big, embed.Embedding) and not m.big.sparse_as_dense
+    assert isinstance(m.small, embed.Embedding) and m.small.sparse_as_dense
+    assert m.big.embeddings.shape == (1, 8)            # dummy [1, dim] graph variable (exb.py:430-432)
+    assert m.small.embeddings.shape == (10, 4)
+    for name in ("save", "save_weights", "load_weights", "save_as_original_model"):
+        assert hasattr(m, name)
+
+
+def test_train_checkpoint_export(cpu_context):
+    import openembedding_b200.torch as embed
+    torch.manual_seed(0)
+    m = embed.distributed_model(_Net())
+    opt = embed.distributed_optimizer(torch.optim.Adagrad(m.parameters(), lr=0.1, initial_accumulator_value=0.1))
+    x, y, t = torch.randint(0, 1000, (64,)), torch.randint(0, 10, (64,)), torch.rand(64)
+    first = None
+    for _ in range(20):
+        loss = ((m(x, y) - t) ** 2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+        first = first if first is not None else float(loss)
+    assert float(loss) < first
+    d = tempfile.mkdtemp()
+    m.save_weights(d + "/w")
+    assert os.path.exists(d + "/w.openembedding/openembedding/model_meta")
+    snap = m.big(x).detach().clone()
+    for _ in range(3):
+        loss = ((m(x, y) - t) ** 2).mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+    assert not torch.equal(m.big(x).detach(), snap)
+    m.load_weights(d + "/w")
+    assert torch.equal(m.big(x).detach(), snap)
+    m.save(d + "/saved", include_optimizer=False)
+    assert os.path.exists(d + "/saved/openembedding/model_meta") and os.path.exists(d + "/saved/model.pt")
+    plain = m.save_as_original_model(d + "/plain.pt")
+    assert type(plain.big) is torch.nn.Embedding and plain.big.weight.shape == (1000, 8)
+    assert torch.allclose(plain.big.weight[x], snap)
+    again = torch.load(d + "/plain.pt", weights_only=False)
+    assert torch.allclose(again(x, y), m(x, y).detach().cpu(), atol=1e-6)
+    with pytest.raises(ValueError):
+        m.save_as_original_model(d + "/p2.pt", include_optimizer=True)
+
+
+def test_hash_embedding_and_errors(cpu_context):
+    import openembedding_b200.torch as embed
+    h = embed.Embedding(-1, 4, embeddings_initializer="zeros")
+    ids = torch.tensor([0, 2 ** 62, 12345678901234])
+    assert torch.equal(h(ids), torch.zeros(3, 4))
+    with pytest.raises(ValueError):
+        embed.Embedding(100, 4, embeddings_regularizer=lambda w: w.sum())        # explicit=True rejects it
+    embed.Embedding(100, 4, embeddings_regularizer=lambda w: w.sum(), explicit=False)
+    with pytest.raises(ValueError):
+        embed.Embedding(0, 4)
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    with pytest.raises(ValueError):
+        embed.distributed_optimizer(torch.optim.Adam(p, amsgrad=True))
+    with pytest.raises(ValueError):
+        embed.distributed_optimizer(torch.optim.RMSprop(p, centered=True))
+    with pytest.raises(ValueError):
+        embed.distributed_optimizer(torch.optim.NAdam(p))       # wrapped by the reference, no server impl
+    with pytest.raises(ValueError):
+        plain = embed.Embedding(-1, 4)
+        wrap = torch.nn.Sequential(plain)
+        embed.save_as_original_model(wrap, tempfile.mkdtemp() + "/x.pt")   # hash tables cannot be exported
+
+
+def test_variable_verbs_and_sum_semantics(cpu_context):
+    import openembedding_b200.torch as embed
+    v = embed.Variable(initializer={"category": "constant", "value": 1.0}, shape=(50, 3))
+    v.set_server_optimizer({"category": "sgd", "learning_rate": 0.5})
+    idx = torch.tensor([3, 3, 7])
+    fake = v.push_gradients(idx, torch.ones(3, 3))
+    assert fake.shape == v.graph_var.shape
+    v.update_weights(fake)
+    out = v.sparse_read(torch.tensor([3, 7, 9]))
+    assert torch.allclose(out[0], torch.full((3,), 0.0)) and torch.allclose(out[1], torch.full((3,), 0.5))
+    assert torch.allclose(out[2], torch.ones(3))
+    assert v.prefetch(idx) is not None
+    dv = embed.distributed_variable(initializer="ones", shape=(5, 2), sparse_as_dense=True)
+    assert dv.sparse_as_dense and dv.sparse_read(torch.tensor([1, 1])).shape == (2, 2)
+    with pytest.raises(ValueError):
+        dv.prefetch(idx)
+
+
+def test_all_optimizer_classes(cpu_context):
+    import openembedding_b200.torch as embed
+    for cls, kw in [(embed.Adadelta, {}), (embed.Adagrad, {"lr": 0.1}), (embed.Adam, {}), (embed.Adamax, {}),
+                    (embed.RMSprop, {}), (embed.SGD, {"lr": 0.1, "momentum": 0.9}), (embed.FtrlDistributed, {"lr": 0.1})]:
+        e = embed.Embedding(100, 4)
+        lin = torch.nn.Linear(4, 1)
+        opt = cls(list(e.parameters()) + list(lin.parameters()), **kw)
+        x = torch.randint(0, 100, (32,))
+        l0 = None
+        for _ in range(15):
+            loss = (lin(e(x)).squeeze(-1) - 1.0).pow(2).mean()
+            opt.zero_grad(); loss.backward(); opt.step()
+            l0 = l0 if l0 is not None else float(loss)
+        assert float(loss) < l0, cls.__name__
+    with pytest.raises(ValueError):
+        embed.Nadam([torch.nn.Parameter(torch.zeros(1))])
+
+
+def test_pulling_prefetches_ids(cpu_context):
+    import openembedding_b200.torch as embed
+    e = embed.Embedding(100, 4, name="C1")
+    m = torch.nn.Sequential(e)
+    data = [({"C1": torch.randint(0, 100, (8,)), "I1": torch.rand(8)}, torch.rand(8)) for _ in range(5)]
+    got = list(embed.pulling(data, m))
+    assert len(got) == 5 and all(torch.equal(a[0]["C1"], b[0]["C1"]) for a, b in zip(got, data))
+    assert len(list(embed.pulling(data, m, steps=3))) == 3
