@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -44,6 +45,7 @@ struct GemmEpi {
     __nv_bfloat16* outT; long long ldoT;
     const __nv_bfloat16* mask; long long ldmask;
     const float* dlogit; const float* S; const float* emb; long long ldemb;
+    unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) [start, setup, first-full, mainloop, epilogue]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,7 +105,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, (BN <= 64 ? 2 : 1))
 exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmT,
                         GemmEpi E, int num_k_blocks, int k_blocks_per_split) {
+    static_assert(BN == 64, "the TMA-store epilogue stages one 64-column tile per warp");
     constexpr int B_BYTES = BN * BK * 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases; do not rely on the toolchain for it
@@ -117,6 +121,9 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+    const bool dbg = E.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define GSTAMP(i) do { if (dbg) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); E.dbg[i] = _t; } } while (0)
+    if (threadIdx.x == 0) GSTAMP(0);
     const int kb0 = blockIdx.z * k_blocks_per_split;
     const int kb1 = min(num_k_blocks, kb0 + k_blocks_per_split);
     const int nkb = kb1 - kb0;
@@ -136,6 +143,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) GSTAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer
@@ -156,6 +164,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
+                if (i == 0) GSTAMP(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -167,79 +176,130 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-        // TMEM hands every thread one ROW (32 consecutive columns). Stores/loads in that layout
-        // touch 32 different lines per instruction, so each warp transposes its 32x32 block
-        // through shared memory (the pipeline stages are free once tmem_full fired) and does
-        // the fused math + global traffic with lanes along the COLUMNS (128-byte rows).
+        // TMEM hands every thread one output ROW (32 consecutive columns per tcgen05.ld). The fused
+        // math runs in that layout; operands it needs (relu mask / FM terms) are fetched BEFORE the
+        // accumulator is awaited, so their latency hides behind the main loop. Results leave through
+        // 128B-swizzled shared-memory tiles and ONE TMA store (or TMA reduce-add for split-K) per
+        // warp: no per-thread global stores, full-line writes, asynchronous to the issuing warp.
         const int q = warp & 3;
-        const int row0 = m_blk * BM + q * 32;
-        bool ok = true;
-        if (nkb > 0) ok = mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+        const int row0 = m_blk * BM + q * 32, row = row0 + lane;
+        const bool rv = row < E.M;
+        uint8_t* wstage = smem + (warp - 2) * 12288;          // per warp: 8 KB out tile(s) + 4 KB outT tile
+        uint8_t* tstage = wstage + 8192;
+        const bool f32out = (E.mode == EPI_DW || E.mode == EPI_DX_FM);
+        bool ok = true, waited = false;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int n0 = n_blk * BN + c0;
+            // ---- issue the global reads of this chunk
+            uint4 mk[4];
+            float4 e4[8], s4[8];
+            float dl = 0.f;
+            if (E.mode == EPI_DX && rv) {
+                const uint4* mp = reinterpret_cast<const uint4*>(E.mask + (size_t)row * E.ldmask + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mk[j] = mp[j];
+            }
+            const bool fm = (E.mode == EPI_DX_FM) && rv && (n0 + 31 < E.fm_cols);
+            if (fm) {
+                const float4* ep = reinterpret_cast<const float4*>(E.emb + (size_t)row * E.ldemb + n0);
+                const float* sbase = E.S + (size_t)row * E.D;
+                dl = E.dlogit[row];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    e4[j] = ep[j];
+                    s4[j] = *reinterpret_cast<const float4*>(sbase + ((n0 + 4 * j) % E.D));
+                }
+            }
+            if (!waited) {
+                if (nkb > 0) ok = mbar_wait(tmem_full, 0);
+                if (warp == 2 && lane == 0) GSTAMP(3);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                waited = true;
+            }
             uint32_t v[32];
             if (nkb > 0 && ok) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
+            // ---- fused math, lane == output row
+            const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(mk);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
-            __syncwarp();
-            const int n = n_blk * BN + c0 + lane;
-            // issue every global read of the block first (32 independent loads per lane in flight)
-            float aux[32];
-            if (E.mode == EPI_DX) {
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr)
-                    aux[rr] = (row0 + rr < E.M) ? __bfloat162float(E.mask[(size_t)(row0 + rr) * E.ldmask + n]) : 0.f;
-            } else if (E.mode == EPI_DX_FM) {
-                const bool fm = n < E.fm_cols;
-                const int dcol = n % E.D;
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int row = row0 + rr;
-                    aux[rr] = (fm && row < E.M) ? (E.S[(size_t)row * E.D + dcol] - E.emb[(size_t)row * E.ldemb + n]) : 0.f;
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]);
+                const int n = n0 + j;
+                if (E.mode == EPI_FWD) {
+                    if (E.relu) x = fmaxf(x, 0.f);
+                    if (n == E.ones_col) x = 1.f;
+                    if (n >= E.N) x = 0.f;
+                } else if (E.mode == EPI_DX) {
+                    if (!rv || !(__bfloat162float(mh[j]) > 0.f) || n == E.ones_col || n >= E.N) x = 0.f;
+                } else if (fm) {
+                    const float* ef = reinterpret_cast<const float*>(e4);
+                    const float* sf = reinterpret_cast<const float*>(s4);
+                    x += dl * (sf[j] - ef[j]);
                 }
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr)
-                    if (fm && row0 + rr < E.M) aux[rr] *= E.dlogit[row0 + rr];
+                v[j] = __float_as_uint(x);
             }
+            // ---- registers -> swizzled staging tile (rows of 128 bytes, 16-byte chunk index ^ (row & 7))
+            if (f32out) {
+                uint8_t* tile = wstage + (c0 >> 5) * 4096;       // [32 rows][32 fp32]
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-                const int row = row0 + rr;
-                float x = stg[rr * 33 + lane];
-                if (row < E.M) {
-                    if (E.mode == EPI_FWD) {
-                        if (E.relu) x = fmaxf(x, 0.f);
-                        if (n == E.ones_col) x = 1.f;
-                        if (n >= E.N) x = 0.f;
-                        reinterpret_cast<__nv_bfloat16*>(E.out)[(size_t)row * E.ldo + n] = __float2bfloat16_rn(x);
-                    } else if (E.mode == EPI_DX) {
-                        if (!(aux[rr] > 0.f) || n == E.ones_col || n >= E.N) x = 0.f;
-                        reinterpret_cast<__nv_bfloat16*>(E.out)[(size_t)row * E.ldo + n] = __float2bfloat16_rn(x);
-                    } else if (E.mode == EPI_DW) {
-                        if (n < E.N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(E.out) + (size_t)row * E.ldo + n), "f"(x) : "memory");
-                    } else {   // EPI_DX_FM
-                        x += aux[rr];
-                        if (n < E.N) reinterpret_cast<float*>(E.out)[(size_t)row * E.ldo + n] = x;
+                for (int t = 0; t < 8; ++t)
+                    *reinterpret_cast<uint4*>(tile + lane * 128 + ((t ^ (lane & 7)) << 4)) =
+                        make_uint4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && E.fm_cols != -7) {
+                    if (E.mode == EPI_DW)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmO), "r"(smem_u32(tile)), "r"(n0), "r"(row0) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmO), "r"(smem_u32(tile)), "r"(n0), "r"(row0) : "memory");
+                }
+            } else {
+                uint8_t* tile = wstage;                           // [32 rows][64 bf16], both chunks
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * u]), __uint_as_float(v[8 * t + 2 * u + 1]));
+                        pk[u] = *reinterpret_cast<uint32_t*>(&h2);
                     }
+                    const int chunk = (c0 >> 3) + t;
+                    *reinterpret_cast<uint4*>(tile + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
-                if (E.outT) stg[rr * 33 + lane] = x;
-            }
-            __syncwarp();
-            if (E.outT && row0 + lane < E.M) {   // lanes = consecutive rows: coalesced transposed copy
+                if (E.outT) {                                     // [64 n][32 rows] bf16: lanes along the row axis
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    E.outT[(size_t)(n_blk * BN + c0 + j) * E.ldoT + row0 + lane] = __float2bfloat16_rn(stg[lane * 33 + j]);
+                    for (int j = 0; j < 32; ++j)
+                        *reinterpret_cast<__nv_bfloat16*>(tstage + (c0 + j) * 64 + lane * 2) = __float2bfloat16_rn(__uint_as_float(v[j]));
+                }
             }
-            __syncwarp();
         }
+        if (!f32out) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && E.fm_cols != -7) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(&tmO), "r"(smem_u32(wstage)), "r"(n_blk * BN), "r"(row0) : "memory");
+                if (E.outT)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmT), "r"(smem_u32(tstage)), "r"(row0), "r"(n_blk * BN) : "memory");
+            }
+        }
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        if (warp == 2 && lane == 0) GSTAMP(4);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x == 0) GSTAMP(5);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -252,7 +312,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 thread_local std::string g_gemm_err;
 
+bool make_map_ex(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* ptr, long long rows, long long cols,
+                 long long ld, int box_cols, int box_rows, CUtensorMapSwizzle sw);
+
 bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    return make_map_ex(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, rows, cols, ld, BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+bool make_map_ex(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* ptr, long long rows, long long cols,
+                 long long ld, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -263,11 +331,11 @@ bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols,
         g_encode = (EncodeTiledFn)fn;
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         g_gemm_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r);
@@ -290,21 +358,30 @@ const char* exb_gemm_last_error() { return g_gemm_err.c_str(); }
 int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M, int N, int K, int mode, int relu,
                      int ones_col, uint64_t out, long long ldo, uint64_t outT, long long ldoT, uint64_t mask,
                      long long ldmask, uint64_t dlogit, uint64_t S, uint64_t emb, long long ldemb, int fm_cols, int D,
-                     int splits, uint64_t stream) {
+                     int splits, uint64_t stream, uint64_t dbg) {
     if (K % BK != 0 || lda % 8 != 0 || ldb % 8 != 0) { g_gemm_err = "gemm: K %% 64 / ld %% 8 violated"; return -1; }
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, (const void*)A, M, K, lda, BM)) return -1;
-    const int BN = (N >= 1024) ? 256 : 64;
+    const int BN = 64;   // a BN=256 variant measured slower: the per-CTA epilogue dominated (profiles/gemm.md)
     if (!make_map(&tmB, (const void*)B, N, K, ldb, BN)) return -1;
+    CUtensorMap tmO, tmT;
+    const bool f32out = (mode == EPI_DW || mode == EPI_DX_FM);
+    if (f32out) {   // fp32 [M, N] (ld ldo): 32x32 boxes = 128-byte rows
+        if (!make_map_ex(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (const void*)out, M, N, ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    } else {        // bf16 [M, ceil64(N)] : 64x32 boxes = 128-byte rows
+        if (!make_map_ex(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)out, M, (N + 63) / 64 * 64, ldo, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
+    tmT = tmO;
+    if (outT && !make_map_ex(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)outT, (N + 63) / 64 * 64, M, ldoT, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     GemmEpi E;
     E.mode = mode; E.relu = relu; E.ones_col = ones_col; E.fm_cols = fm_cols; E.M = M; E.N = N; E.D = D > 0 ? D : 1; E._pad = 0;
     E.out = (void*)out; E.ldo = ldo; E.outT = (__nv_bfloat16*)outT; E.ldoT = ldoT;
     E.mask = (const __nv_bfloat16*)mask; E.ldmask = ldmask;
     E.dlogit = (const float*)dlogit; E.S = (const float*)S; E.emb = (const float*)emb; E.ldemb = ldemb;
+    E.dbg = (unsigned long long*)dbg;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
-        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<256>());
         attr_set = true;
     }
     const int nkb = K / BK;
@@ -313,10 +390,7 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    if (BN == 64)
-        exb_gemm_tcgen05_kernel<64><<<grid, NUM_THREADS, gemm_smem<64>(), (cudaStream_t)stream>>>(tmA, tmB, E, nkb, per);
-    else
-        exb_gemm_tcgen05_kernel<256><<<grid, NUM_THREADS, gemm_smem<256>(), (cudaStream_t)stream>>>(tmA, tmB, E, nkb, per);
+    exb_gemm_tcgen05_kernel<64><<<grid, NUM_THREADS, gemm_smem<64>(), (cudaStream_t)stream>>>(tmA, tmB, tmO, tmT, E, nkb, per);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(err); return -1; }
     return 0;

@@ -22,7 +22,8 @@ def _lib():
         lib.exb_gemm_bf16_nt.restype = c_int
         lib.exb_gemm_bf16_nt.argtypes = [c_uint64, c_longlong, c_uint64, c_longlong, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_uint64, c_longlong, c_uint64, c_longlong, c_uint64, c_longlong,
-                                         c_uint64, c_uint64, c_uint64, c_longlong, c_int, c_int, c_int, c_uint64]
+                                         c_uint64, c_uint64, c_uint64, c_longlong, c_int, c_int, c_int, c_uint64,
+                                         c_uint64]
         lib.exb_gemm_last_error.restype = ctypes.c_char_p
         _proto_done = True
     return lib
@@ -33,7 +34,7 @@ def _p(t):
 
 
 def gemm_nt(A, B, M, N, K, out, mode=EPI_FWD, relu=False, ones_col=-1, outT=None, mask=None, dlogit=None, S=None,
-            emb=None, fm_cols=0, D=1, splits=1, stream=None):
+            emb=None, fm_cols=0, D=1, splits=1, stream=None, dbg=None):
     """A: [>=M, lda] bf16 view, B: [>=N, ldb] bf16 view (both row-major, K contiguous)."""
     lib = _lib()
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -42,7 +43,7 @@ def gemm_nt(A, B, M, N, K, out, mode=EPI_FWD, relu=False, ones_col=-1, outT=None
     rc = lib.exb_gemm_bf16_nt(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, mode, int(relu), ones_col,
                               out.data_ptr(), out.stride(0), _p(outT), outT.stride(0) if outT is not None else 0,
                               _p(mask), mask.stride(0) if mask is not None else 0, _p(dlogit), _p(S), _p(emb),
-                              emb.stride(0) if emb is not None else 0, fm_cols, D, splits, st)
+                              emb.stride(0) if emb is not None else 0, fm_cols, D, splits, st, _p(dbg))
     if rc != 0:
         raise RuntimeError("exb_gemm_bf16_nt: " + lib.exb_gemm_last_error().decode())
     return out

@@ -20,7 +20,8 @@ def test_fwd_relu_ones_transposed(M, N, K):
     A, B = _mk(M, K, seed=1), _mk(Np, K, scale=0.1, seed=2)
     B[N:] = 0
     out = torch.full((M, Np), 7.0, device="cuda", dtype=torch.bfloat16)
-    outT = torch.full((Np, M), 7.0, device="cuda", dtype=torch.bfloat16)
+    Mp = (M + 7) // 8 * 8        # TMA store: leading dimensions must be multiples of 16 bytes
+    outT = torch.full((Np, Mp), 7.0, device="cuda", dtype=torch.bfloat16)[:, :M]
     ones_col = N - 1
     gemm_nt(A, B, M, N, K, out, mode=EPI_FWD, relu=True, ones_col=ones_col, outT=outT)
     torch.cuda.synchronize()
