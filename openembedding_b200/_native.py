@@ -122,6 +122,7 @@ def cuda():
         P(lib, "exb_plan_set_peer_inbox", c_int, [c_void_p, c_int, c_uint64])
         P(lib, "exb_plan_commit", c_int, [c_void_p])
         P(lib, "exb_plan_grid", c_int, [c_void_p, c_int])
+        P(lib, "exb_plan_set_trace", c_int, [c_void_p, c_uint64])
         P(lib, "exb_pull", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_uint64])
         P(lib, "exb_push_update", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_uint64])
         _cuda = lib

@@ -133,7 +133,7 @@ template <int KIND>
 __device__ __noinline__ void apply_rows_bulk_k(const TableDev& T, const PlanDev& P, float* accbase,
                                                unsigned long long key, unsigned long long row, unsigned h,
                                                unsigned cnt, int flag, int lane, unsigned char* buf,
-                                               WarpMeta* M) {
+                                               WarpMeta* M, int nrows, unsigned long long* trt) {
     const int wstride = T.wstride, sstride = T.sstride, dim = T.dim, nslots = T.nslots, nsc = T.nscalars;
     const unsigned wb = (unsigned)wstride * 4u, sb = (unsigned)sstride * 4u;
     const int R = min(32, (int)(EXB_APPLY_WARP_BUF / (2u * wb + sb)));
@@ -147,7 +147,7 @@ __device__ __noinline__ void apply_rows_bulk_k(const TableDev& T, const PlanDev&
     float* wbuf = reinterpret_cast<float*>(buf);
     float* sbuf = reinterpret_cast<float*>(buf + (size_t)R * wb);
     float* abuf = reinterpret_cast<float*>(buf + (size_t)R * (wb + sb));
-    for (int r0 = 0; r0 < 32; r0 += R) {
+    for (int r0 = 0; r0 < nrows; r0 += R) {
         // ---- gather: lane group g fetches rows g, g+RP, ... of the pass
         for (int jj = lane / lpr; jj < R; jj += RP) {
             const int rr = r0 + jj;
@@ -165,6 +165,7 @@ __device__ __noinline__ void apply_rows_bulk_k(const TableDev& T, const PlanDev&
         }
         cp_async_commit_wait();
         __syncwarp();
+        if (trt && lane == 0) trt[5] = globaltimer_ns();
         // ---- math out of shared memory, results go straight to global
         for (int jj = lane / lpr; jj < R; jj += RP) {
             const int rr = r0 + jj;
@@ -213,18 +214,17 @@ __device__ __noinline__ void apply_rows_bulk_k(const TableDev& T, const PlanDev&
 __device__ __forceinline__ void apply_rows_bulk(const TableDev& T, const PlanDev& P, float* accbase,
                                                 unsigned long long key, unsigned long long row, unsigned h,
                                                 unsigned cnt, int flag, int lane, unsigned char* buf,
-                                                WarpMeta* M, unsigned long long* mbar, unsigned& parity) {
-    (void)mbar; (void)parity;
+                                                WarpMeta* M, int nrows, unsigned long long* trt) {
     switch (T.opt.kind) {   // warp uniform
-        case OPT_ADADELTA: apply_rows_bulk_k<OPT_ADADELTA>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_ADAGRAD: apply_rows_bulk_k<OPT_ADAGRAD>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_ADAM: apply_rows_bulk_k<OPT_ADAM>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_ADAMAX: apply_rows_bulk_k<OPT_ADAMAX>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_FTRL: apply_rows_bulk_k<OPT_FTRL>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_RMSPROP: apply_rows_bulk_k<OPT_RMSPROP>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_SGD: apply_rows_bulk_k<OPT_SGD>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        case OPT_TEST: apply_rows_bulk_k<OPT_TEST>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
-        default: apply_rows_bulk_k<OPT_DEFAULT>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M); break;
+        case OPT_ADADELTA: apply_rows_bulk_k<OPT_ADADELTA>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_ADAGRAD: apply_rows_bulk_k<OPT_ADAGRAD>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_ADAM: apply_rows_bulk_k<OPT_ADAM>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_ADAMAX: apply_rows_bulk_k<OPT_ADAMAX>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_FTRL: apply_rows_bulk_k<OPT_FTRL>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_RMSPROP: apply_rows_bulk_k<OPT_RMSPROP>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_SGD: apply_rows_bulk_k<OPT_SGD>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        case OPT_TEST: apply_rows_bulk_k<OPT_TEST>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
+        default: apply_rows_bulk_k<OPT_DEFAULT>(T, P, accbase, key, row, h, cnt, flag, lane, buf, M, nrows, trt); break;
     }
 }
 

@@ -298,29 +298,40 @@ __global__ void exb_refresh_bf16_kernel(const float* W, __nv_bfloat16* Wb, __nv_
     }
 }
 
-// ---- P2P all-reduce (sum) over peer-mapped buffers -------------------------------------
+// ---- P2P all-reduce (sum) over peer-mapped buffers, fused with the dense optimizer ------
+// ONE persistent kernel (grid <= resident CTAs):
+//   signal "my gradients are complete"  | every CTA polls its LOCAL flag row for all peers
+//   reduce-scatter + all-gather in one pass: this rank sums its 1/W slice with peer LOADS
+//     from every rank and peer-STORES the sum back into every rank's buffer in place (the
+//     slice of a buffer is read only by its reducing rank, by the very thread that then
+//     overwrites it, so no scratch and no barrier between the two halves)
+//   last CTA to finish signals "my stores have landed" | every CTA polls for all peers
+//   Adagrad over the whole (now identical on every rank) gradient, fused behind the wait.
+// Two flag exchanges per call instead of the three barrier kernels + two memcpys of the
+// first version (89 us -> see profiles/). Flags are monotonically increasing epochs.
 struct ArArgs {
     float* buf[8];          // every rank's gradient buffer (peer mapped), index = rank
     unsigned* flags[8];     // every rank's flag array [8]
     unsigned* epoch;        // local
+    unsigned* gcount;       // local: CTA arrival counter
     int* status;
     long long n;
     int W, rank;
 };
 
-__device__ __forceinline__ void ar_barrier(const ArArgs& a) {   // executed by CTA 0 only
-    __threadfence_system();
-    __syncthreads();
-    const unsigned e = *(volatile unsigned*)a.epoch + 1;
-    __syncthreads();
-    if ((int)threadIdx.x < a.W) {
+__device__ __forceinline__ void ar_signal(const ArArgs& a, unsigned e) {   // threads < W of one CTA
+    if ((int)threadIdx.x < a.W)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.flags[threadIdx.x][a.rank]), "r"(e) : "memory");
+}
+__device__ __forceinline__ void ar_wait(const ArArgs& a, unsigned e) {     // every CTA
+    if ((int)threadIdx.x < a.W) {
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (unsigned it = 0;; ++it) {
             unsigned v;
             asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&a.flags[a.rank][threadIdx.x]) : "memory");
             if ((int)(v - e) >= 0) break;
+            __nanosleep(20);
             if ((it & 255u) == 255u) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                 if (t1 - t0 > 4000000000ull) { atomicCAS(a.status, 0, 2); break; }
@@ -329,39 +340,57 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a) {   // executed by C
         asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) *(volatile unsigned*)a.epoch = e;
-    __threadfence_system();
-    __syncthreads();
 }
 
-// Five launches, stream order is the grid-wide barrier:
-//   barrier | reduce-scatter (peer LOADS of this rank's slice from every peer) | barrier |
-//   all-gather (peer STORES of the reduced slice into every peer) | barrier
-__global__ void exb_ar_barrier_kernel(ArArgs a) { ar_barrier(a); }
-
-__global__ void __launch_bounds__(256) exb_ar_reduce_scatter_kernel(ArArgs a, float* scratch) {
+__global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, float* theta, float* accum, float lr, float eps) {
+    __shared__ int s_last;
+    const unsigned e0 = *(volatile unsigned*)a.epoch;
+    if (blockIdx.x == 0) ar_signal(a, e0 + 1);     // earlier kernels of this stream wrote the gradients
+    ar_wait(a, e0 + 1);
     const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
     const long long lo = per * a.rank, hi = min(a.n, lo + per);
     for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
          i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < a.W) v[r] = __ldcg(reinterpret_cast<const float4*>(a.buf[r] + i));   // peer loads over NVLink
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int r = 0; r < a.W; ++r) {
-            const float4 v = *reinterpret_cast<const float4*>(a.buf[r] + i);   // peer load over NVLink
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        *reinterpret_cast<float4*>(scratch + (i - lo)) = s;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < a.W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < a.W) __stcg(reinterpret_cast<float4*>(a.buf[r] + i), s);             // peer stores
     }
-}
-
-__global__ void __launch_bounds__(256) exb_ar_all_gather_kernel(ArArgs a, const float* scratch) {
-    const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
-    const long long lo = per * a.rank, hi = min(a.n, lo + per);
-    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");     // cumulative over the CTA's peer stores
+        s_last = atomicAdd(a.gcount, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            *(volatile unsigned*)a.gcount = 0;
+            *(volatile unsigned*)a.epoch = e0 + 2;
+        }
+        __syncthreads();
+        ar_signal(a, e0 + 2);
+    }
+    ar_wait(a, e0 + 2);
+    if (theta == nullptr) return;
+    const float* grad = a.buf[a.rank];
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < a.n;
          i += (long long)gridDim.x * blockDim.x * 4) {
-        const float4 s = *reinterpret_cast<const float4*>(scratch + (i - lo));
-#pragma unroll 8
-        for (int r = 0; r < a.W; ++r) *reinterpret_cast<float4*>(a.buf[r] + i) = s;   // peer store
+        float4 g = __ldcg(reinterpret_cast<const float4*>(grad + i));
+        float4 ac = *reinterpret_cast<float4*>(accum + i);
+        float4 w = *reinterpret_cast<float4*>(theta + i);
+        ac.x += g.x * g.x; ac.y += g.y * g.y; ac.z += g.z * g.z; ac.w += g.w * g.w;
+        w.x -= lr * g.x / (sqrtf(ac.x) + eps); w.y -= lr * g.y / (sqrtf(ac.y) + eps);
+        w.z -= lr * g.z / (sqrtf(ac.z) + eps); w.w -= lr * g.w / (sqrtf(ac.w) + eps);
+        *reinterpret_cast<float4*>(accum + i) = ac;
+        *reinterpret_cast<float4*>(theta + i) = w;
     }
 }
 
@@ -423,19 +452,23 @@ int exb_refresh_bf16(uint64_t W, uint64_t Wb, uint64_t WTb, int R, int C, uint64
 }
 
 // all-reduce (sum, in place) of a flat fp32 buffer of n elements (n % 4 == 0, 16-byte aligned)
-// that every rank has peer-mapped; bufs/flags: W pointers each; epoch/status: local words.
-int exb_allreduce_sum(const uint64_t* bufs, const uint64_t* flags, uint64_t epoch, uint64_t status, uint64_t scratch,
-                      long long n, int W, int rank, int ctas, uint64_t stream) {
+// that every rank has peer-mapped; bufs/flags: W pointers each; epoch/gcount/status: local words.
+// theta/accum != 0: Adagrad step on the reduced gradient inside the same kernel.
+int exb_allreduce_adagrad(const uint64_t* bufs, const uint64_t* flags, uint64_t epoch, uint64_t gcount, uint64_t status,
+                          long long n, int W, int rank, int ctas, uint64_t theta, uint64_t accum, float lr, float eps,
+                          uint64_t stream) {
     ArArgs a;
     for (int i = 0; i < 8; ++i) { a.buf[i] = i < W ? (float*)bufs[i] : nullptr; a.flags[i] = i < W ? (unsigned*)flags[i] : nullptr; }
-    a.epoch = (unsigned*)epoch; a.status = (int*)status; a.n = n; a.W = W; a.rank = rank;
+    a.epoch = (unsigned*)epoch; a.gcount = (unsigned*)gcount; a.status = (int*)status; a.n = n; a.W = W; a.rank = rank;
+    if (n % 4) { g_dense_err = "allreduce: n must be a multiple of 4"; return -1; }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_ar_fused_kernel, 256, 0);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (ctas < 1) ctas = 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
-    exb_ar_reduce_scatter_kernel<<<ctas, 256, 0, st>>>(a, (float*)scratch);
-    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
-    exb_ar_all_gather_kernel<<<ctas, 256, 0, st>>>(a, (const float*)scratch);
-    exb_ar_barrier_kernel<<<1, 32, 0, st>>>(a);
+    if (ctas > sms) ctas = sms;             // CTAs wait on each other: keep the grid resident
+    exb_ar_fused_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(a, (float*)theta, (float*)accum, lr, eps);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;

@@ -698,6 +698,7 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     d.epoch = (unsigned*)(e->sync_local + OFF_EPOCH);
     d.status = (int*)(e->sync_local + OFF_STATUS);
     d.stats = (unsigned long long*)(e->sync_local + OFF_STATS);
+    d.trace = nullptr;
     // ---- launch geometry: persistent push kernel must be fully resident
     p->smem_pull = exb_smem_total(PT, F, false);
     p->smem_push = exb_smem_total(PT, F, true);
@@ -710,7 +711,9 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_push_update_kernel, 256, p->smem_push);
     if (occ < 1) occ = 1;
-    int resident = e->sms * std::min(occ, 4);
+    int per_sm = std::min(occ, 4);
+    if (const char* ev = getenv("EXB_PUSH_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(ev)));
+    int resident = e->sms * per_sm;
     int want = std::max(1, (d.num_tasks * std::max(1, W / 2 + 1) + 7) / 8);
     p->grid_push = std::min(resident, want);
     int occ_pull = 1;
@@ -751,6 +754,8 @@ int exb_plan_commit(void* ph) {
     }
     return 0;
 }
+// per-warp phase trace of the push kernel: buffer of grid_push*8*EXB_TRACE_SLOTS u64 (0 = off)
+int exb_plan_set_trace(void* ph, uint64_t ptr) { ((Plan*)ph)->d.trace = (unsigned long long*)ptr; return 0; }
 int exb_plan_grid(void* ph, int which) { Plan* p = (Plan*)ph; return which ? p->grid_push : p->grid_pull; }
 
 int exb_pull(void* ph, uint64_t ids, uint64_t out, int n_rows, uint64_t stream) {

@@ -68,7 +68,9 @@ struct PlanDev {
     unsigned* epoch;                                // device-resident barrier epoch
     int* status;                                    // 0 ok; else first error code
     unsigned long long* stats;                      // [0] pull ids, [1] push ids, [2] unique rows updated
+    unsigned long long* trace;                      // optional per-warp %globaltimer trace (EXB_TRACE_SLOTS per warp)
 };
+#define EXB_TRACE_SLOTS 32
 
 enum ExbStatus : int {
     EXB_OK = 0,
@@ -99,6 +101,12 @@ __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timer read that cannot issue before `dep` has been produced (scoreboard dependency)
+__device__ __forceinline__ unsigned long long globaltimer_after(unsigned long long dep) {
+    unsigned long long t;
+    asm volatile("{ .reg .b64 d; mov.b64 d, %1; mov.u64 %0, %%globaltimer; }" : "=l"(t) : "l"(dep));
     return t;
 }
 // fire-and-forget vector reduction (sm_90+): 4 fp32 adds in one L2 atomic transaction
@@ -137,6 +145,9 @@ __device__ __forceinline__ int shard_of_rank(const TableDev& T, int rank, int W)
     return (rank - T.shard_base % W + W) % W;
 }
 
+// NEVER read shared words through `volatile`: it lowers to LDG.STRONG.SYS, and those loads
+// took ~5 us each in the apply phase (trace: 15.9 us -> 4.4 us per task after switching the
+// four dependent loads to ld.global.cg / ld.relaxed.gpu).
 // Polling loads are RELAXED (no per-iteration L1 invalidate: `ld.acquire` lowers to
 // LDG + CCTL.IVALL, and a spinning thread would keep flushing the L1 that co-resident
 // CTAs are still working out of); one acquire fence is issued after the loop exits.
@@ -150,6 +161,11 @@ __device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
@@ -159,18 +175,22 @@ __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_re
 // the count publication happen.
 template <class MasterFn>
 __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, MasterFn master) {
-    if (sys_scope) __threadfence_system(); else __threadfence();
+    // bar.sync orders every thread's writes before thread 0's fence, and fence + atomic is a
+    // cumulative release: ONE fence per CTA covers the whole CTA (a system fence costs an
+    // NVLink round trip when peer stores are in flight -- 256 of them in series per barrier
+    // was most of the 17-25 us the first version spent here).
     __syncthreads();
     __shared__ unsigned s_gen;
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
+            if (sys_scope) fence_acq_rel_sys(); else fence_acq_rel_gpu();
             unsigned gen = ld_relaxed_gpu_u32(&P.gbar[1]);
             s_gen = gen;
             atomicAdd(&P.gbar[0], 1u);
             unsigned long long t0 = globaltimer_ns();
             unsigned it = 0;
             while (ld_relaxed_gpu_u32(&P.gbar[0]) != gridDim.x) {
-                __nanosleep(32);
+                __nanosleep(20);
                 if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                     set_error(P.status, EXB_ERR_TIMEOUT_GRID);
                     break;
@@ -183,18 +203,17 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
         __syncthreads();
         if (threadIdx.x == 0) {
             P.gbar[0] = 0;
-            __threadfence();
-            st_release_gpu_u32(&P.gbar[1], s_gen + 1);
+            st_release_gpu_u32(&P.gbar[1], s_gen + 1);   // release orders the reset before the new generation
         }
     } else {
         if (threadIdx.x == 0) {
             unsigned gen = ld_relaxed_gpu_u32(&P.gbar[1]);
-            __threadfence();
+            if (sys_scope) fence_acq_rel_sys(); else fence_acq_rel_gpu();
             atomicAdd(&P.gbar[0], 1u);
             unsigned long long t0 = globaltimer_ns();
             unsigned it = 0;
             while (ld_relaxed_gpu_u32(&P.gbar[1]) == gen) {
-                __nanosleep(64);
+                __nanosleep(20);
                 if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                     set_error(P.status, EXB_ERR_TIMEOUT_GRID);
                     break;
@@ -207,18 +226,44 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
 }
 
 // Cross-GPU barrier executed by CTA 0 (all its threads call this). Every rank writes its
-// new epoch into slot [rank] of every peer's flag array with a system-scope release and
-// then polls its own array until all peers have reached the epoch (acquire fence after).
-__device__ __forceinline__ void peer_barrier(const PlanDev& P) {
-    __threadfence_system();
+// new epoch into slot [rank] of every peer's flag array with a system-scope release
+// (cumulative over everything CTA 0 has observed, i.e. the whole grid's peer stores) and,
+// if `wait`, polls its own array until all peers have reached the epoch.
+// wait == false is the "update done" signal at the end of a push: nobody has to stand still
+// for it -- the next kernel that reads peer shards (pull) calls peer_wait() first, by which
+// time the flags have long arrived.
+__device__ __forceinline__ void peer_barrier(const PlanDev& P, bool wait = true) {
     __syncthreads();
-    unsigned e = *(volatile unsigned*)P.epoch + 1;
+    const unsigned e = *(volatile unsigned*)P.epoch + 1;
     __syncthreads();
     if ((int)threadIdx.x < P.W) {
         st_release_sys_u32(&P.flags[threadIdx.x][P.rank], e);
+        if (wait) {
+            unsigned long long t0 = globaltimer_ns();
+            unsigned it = 0;
+            while ((int)(ld_relaxed_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
+                if ((++it & 255u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
+                    set_error(P.status, EXB_ERR_TIMEOUT_PEER);
+                    break;
+                }
+            }
+            fence_acq_rel_sys();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned*)P.epoch = e;
+    __syncthreads();
+}
+
+// Every CTA of a kernel that reads peer shards: wait until all peers have signalled the
+// epoch this rank has reached (their last update is complete and visible).
+__device__ __forceinline__ void peer_wait(const PlanDev& P) {
+    if ((int)threadIdx.x < P.W) {
+        const unsigned e = *(volatile unsigned*)P.epoch;
         unsigned long long t0 = globaltimer_ns();
         unsigned it = 0;
         while ((int)(ld_relaxed_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
+            __nanosleep(20);
             if ((++it & 255u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                 set_error(P.status, EXB_ERR_TIMEOUT_PEER);
                 break;
@@ -226,9 +271,6 @@ __device__ __forceinline__ void peer_barrier(const PlanDev& P) {
         }
         fence_acq_rel_sys();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *(volatile unsigned*)P.epoch = e;
-    __threadfence_system();
     __syncthreads();
 }
 

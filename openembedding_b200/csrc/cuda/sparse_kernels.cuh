@@ -188,6 +188,7 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = P.W;
+    if (W > 1) peer_wait(P);   // peers' last update is complete (deferred half of the push "done" barrier)
     const int wic = threadIdx.x >> 5;
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, false);
     unsigned char* wbuf = stage_end + (size_t)wic * EXB_PULL_WARP_BUF;
@@ -349,7 +350,7 @@ __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, in
         int beg = lane * chunk, end = min(n, beg + chunk);
         int sum = 0;
         for (int i = beg; i < end; ++i)
-            sum += (int)((*(volatile const unsigned*)&cnt[(size_t)i * stride] + 31u) >> 5);
+            sum += (int)((__ldcg(&cnt[(size_t)i * stride]) + 31u) >> 5);
         int incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -358,7 +359,44 @@ __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, in
         int run = incl - sum;
         for (int i = beg; i < end; ++i) {
             s_prefix[i] = run;
-            run += (int)((*(volatile const unsigned*)&cnt[(size_t)i * stride] + 31u) >> 5);
+            run += (int)((__ldcg(&cnt[(size_t)i * stride]) + 31u) >> 5);
+        }
+        if (lane == 31) s_prefix[n] = incl;
+    }
+    __syncthreads();
+}
+
+// unique rows per warp task of the apply phase: what fits the warp's row buffer in ONE pass
+// (dim 64 + Adagrad: 13). Finer tasks than 32 rows balance the phase: with 32-row tasks the
+// slowest warp walked 6 buffer passes while the average warp needed 2.6.
+__device__ __forceinline__ int apply_chunk(const TableDev& T, int use_bulk) {
+    const unsigned need = (2u * (unsigned)T.wstride + (unsigned)T.sstride) * 4u;
+    if (use_bulk && T.vec4 && need <= EXB_APPLY_WARP_BUF) return min(32, (int)(EXB_APPLY_WARP_BUF / need));
+    return 32;
+}
+// block_task_prefix with ceil(cnt / apply_chunk(table)) tasks per table
+__device__ __forceinline__ void block_apply_prefix(const unsigned* cnt, int n, int* s_prefix, int stride,
+                                                   const TableDev* tab, int use_bulk) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (n + 31) / 32;
+        int beg = lane * per, end = min(n, beg + per);
+        int sum = 0;
+        for (int i = beg; i < end; ++i) {
+            const int c = apply_chunk(tab[i], use_bulk);
+            sum += (int)((__ldcg(&cnt[(size_t)i * stride]) + (unsigned)c - 1u) / (unsigned)c);
+        }
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int run = incl - sum;
+        for (int i = beg; i < end; ++i) {
+            s_prefix[i] = run;
+            const int c = apply_chunk(tab[i], use_bulk);
+            run += (int)((__ldcg(&cnt[(size_t)i * stride]) + (unsigned)c - 1u) / (unsigned)c);
         }
         if (lane == 31) s_prefix[n] = incl;
     }
@@ -578,7 +616,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
         grid_barrier(P, true, [&]() {
             for (int i = threadIdx.x; i < W * PT; i += blockDim.x) {
                 int o = i / PT, pt = i - o * PT;
-                unsigned c = *(volatile unsigned*)&P.send_cnt[i * EXB_CTR_STRIDE];
+                unsigned c = __ldcg(&P.send_cnt[i * EXB_CTR_STRIDE]);
                 if (c > S.cap[pt]) c = S.cap[pt];
                 if (o != rank) P.inbox_cnt[o][rank * PT + pt] = c;
                 P.send_cnt[i * EXB_CTR_STRIDE] = 0;
@@ -596,7 +634,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             if (s == rank) continue;  // local ids never travel through the inbox
             const TableDev& T = S.tab[pt];
             const unsigned e = (unsigned)(task - s_prefix[seg]) * 32u + lane;
-            const unsigned n = *(volatile const unsigned*)&mycnt[seg];
+            const unsigned n = __ldcg(&mycnt[seg]);
             const float* src = nullptr;
             float* dst = nullptr;
             int mode = 0;
@@ -623,26 +661,35 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     EXB_STAMP(4);
 
     // ---------------- P5: apply optimizer to every unique row
-    block_task_prefix(P.ucount, PT, s_prefix, EXB_CTR_STRIDE);
+    block_apply_prefix(P.ucount, PT, s_prefix, EXB_CTR_STRIDE, S.tab, P.use_bulk);
     const int ntask5 = s_prefix[PT];
     unsigned n_unique_local = 0;
+    unsigned long long* tr = P.trace ? P.trace + (size_t)warp * EXB_TRACE_SLOTS : nullptr;
+    int trk = 1;
+    if (tr && lane == 0) tr[0] = globaltimer_ns();
     for (int task = warp; task < ntask5; task += nwarps) {
         const int pt = find_segment(s_prefix, PT, task);
         const TableDev& T = S.tab[pt];
-        const unsigned u = (unsigned)(task - s_prefix[pt]) * 32u + lane;
-        const unsigned n = *(volatile unsigned*)&P.ucount[pt * EXB_CTR_STRIDE];
+        const int chunk = apply_chunk(T, P.use_bulk);
+        const unsigned n = __ldcg(&P.ucount[pt * EXB_CTR_STRIDE]);
+        const unsigned u = lane < chunk ? (unsigned)(task - s_prefix[pt]) * (unsigned)chunk + lane : n;
 #ifdef EXB_PROBE
         const bool probe5 = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
         if (probe5) P.stats[22] = globaltimer_ns();
 #endif
+        unsigned long long* trt = (tr && trk + 8 <= EXB_TRACE_SLOTS) ? tr + trk : nullptr;
+        trk += 8;
+        if (trt && lane == 0) { trt[0] = (unsigned long long)task | ((unsigned long long)pt << 32); trt[1] = globaltimer_after(n); }
         unsigned long long key = 0, row = 0;
         unsigned h = 0, cnt = 0;
         int flag = 0;
         if (u < n) {
-            h = P.ulist[S.ulist_off[pt] + u];
+            h = __ldcg(&P.ulist[S.ulist_off[pt] + u]);
+            if (trt && lane == 0) trt[2] = globaltimer_after(h);
             const unsigned long long mo = S.map_off[pt] + h;
-            key = *(volatile unsigned long long*)&P.cmap_keys[mo];
-            cnt = *(volatile unsigned*)&P.cmap_cnt[mo];
+            key = __ldcg(&P.cmap_keys[mo]);
+            cnt = __ldcg(&P.cmap_cnt[mo]);
+            if (trt && lane == 0) trt[3] = globaltimer_after(key + cnt);
             P.cmap_keys[mo] = EXB_EMPTY_KEY;
             P.cmap_cnt[mo] = 0;
             if (!T.is_hash) {
@@ -653,7 +700,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                 unsigned long long* keys = const_cast<unsigned long long*>(T.keys[rank]);
                 unsigned long long mask = T.rows - 1, hh = exb_hash64(key) & mask;
                 for (unsigned long long probe = 0; probe <= mask; ++probe) {
-                    unsigned long long k = *(volatile unsigned long long*)&keys[hh];
+                    unsigned long long k = ld_relaxed_gpu_u64(&keys[hh]);
                     if (k == key) { flag = 1; break; }
                     if (k == EXB_EMPTY_KEY) {
                         unsigned long long prev = atomicCAS(&keys[hh], EXB_EMPTY_KEY, key);
@@ -675,8 +722,10 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
 #ifdef EXB_PROBE
         if (probe5) P.stats[23] = globaltimer_ns() + (row & 0) + (cnt & 0);
 #endif
+        if (trt && lane == 0) trt[4] = globaltimer_after(row + (unsigned)flag);
         if (P.use_bulk && T.vec4 && (2 * T.wstride + T.sstride) * 4 <= EXB_APPLY_WARP_BUF) {
-            apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, mbar, parity);
+            apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, chunk, trt);
+            if (trt && lane == 0) { __threadfence(); trt[6] = globaltimer_ns(); }
             continue;
         }
         switch (T.lpr) {
@@ -696,10 +745,10 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     EXB_STAMP(5);
 
     // ---------------- B3: reset per-step counters; cross-GPU "update done"
-    grid_barrier(P, W > 1, [&]() {
+    grid_barrier(P, false, [&]() {   // P5 wrote local memory only; the sys release is in peer_barrier
         for (int i = threadIdx.x; i < PT; i += blockDim.x) P.ucount[i * EXB_CTR_STRIDE] = 0;
         if (threadIdx.x == 0) atomicAdd(&P.stats[1], (unsigned long long)n_rows * P.F);
-        if (W > 1) peer_barrier(P);
+        if (W > 1) peer_barrier(P, false);   // signal only: the next pull waits (peer_wait)
     });
     EXB_STAMP(6);
 #undef EXB_STAMP

@@ -19,6 +19,7 @@ Model definition = DeepCTR's DeepFM / WDL as used by the reference benchmark
 of the same architecture (used as the numerical reference in tests).
 """
 import ctypes
+import os
 import math
 from ctypes import c_float, c_int, c_longlong, c_void_p
 
@@ -70,9 +71,9 @@ def _lib():
         lib.exb_adagrad_flat.argtypes = [u64, u64, u64, c_longlong, c_float, c_float, u64]
         lib.exb_refresh_bf16.restype = c_int
         lib.exb_refresh_bf16.argtypes = [u64, u64, u64, c_int, c_int, u64]
-        lib.exb_allreduce_sum.restype = c_int
-        lib.exb_allreduce_sum.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64), u64, u64, u64, c_longlong, c_int,
-                                          c_int, c_int, u64]
+        lib.exb_allreduce_adagrad.restype = c_int
+        lib.exb_allreduce_adagrad.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64), u64, u64, u64, c_longlong, c_int,
+                                              c_int, c_int, u64, u64, c_float, c_float, u64]
         lib.exb_dense_last_error.restype = ctypes.c_char_p
         assert lib.exb_prep_args_size() == ctypes.sizeof(_PrepArgs), "PrepArgs ABI mismatch"
         assert lib.exb_head_args_size() == ctypes.sizeof(_HeadArgs), "HeadArgs ABI mismatch"
@@ -146,7 +147,13 @@ class FusedCTR:
         self.segs, self.n_theta = segs, off
         self.theta = torch.zeros(off, dtype=f32, device=dev)
         self.accum = torch.full((off,), float(initial_accumulator_value), dtype=f32, device=dev)
-        self.gtheta = torch.zeros(off, dtype=f32, device=dev)
+        self._ar = None
+        if ctx.world > 1:     # gradients are produced straight into the peer-mapped all-reduce buffer
+            from ..ops.p2p_allreduce import P2PAllReduce
+            self._ar = P2PAllReduce(ctx, off)
+            self.gtheta = self._ar.grad
+        else:
+            self.gtheta = torch.zeros(off, dtype=f32, device=dev)
         gen = torch.Generator(device="cpu").manual_seed(seed)
         fan_in = [nf * embedding_dim + num_dense] + self.hidden
         for l in range(L):
@@ -187,10 +194,10 @@ class FusedCTR:
             o += self.vocab[f]
         self.cache_col = torch.tensor(self.cached or [0], dtype=torch.int32, device=dev)
         self.cache_off = torch.tensor(offs_c or [0], dtype=torch.int64, device=dev)
-        self._ar = None
-        if ctx.world > 1:
-            from ..ops.p2p_allreduce import P2PAllReduce
-            self._ar = P2PAllReduce(ctx, self.gtheta)
+        # push+update runs on a second stream next to the dW GEMMs / dense optimizer (fork after dX1, join at step end)
+        self.overlap = os.environ.get("EXB_OVERLAP", "1") != "0"
+        self._s2 = torch.cuda.Stream(device=dev)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.refresh_weights()
         torch.cuda.synchronize(dev)
 
@@ -206,6 +213,14 @@ class FusedCTR:
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
+    _trace = None          # list of (name, event) when stage tracing is on (tools/mp_timeline.py)
+
+    def _mark(self, name):
+        if self._trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.dev))
+            self._trace.append((name, ev))
+
     def refresh_weights(self):
         dims = [self.K0p] + self.Hp
         for l in range(len(self.hidden)):
@@ -218,19 +233,23 @@ class FusedCTR:
         assert ids.shape == (B, self.nf) and ids.dtype == torch.int64 and ids.is_contiguous()
         self.gtheta.zero_()
         self.loss.zero_()
+        self._mark("start")
         self.group.pull(ids, out=self.X32)
+        self._mark("pull")
         pa = _PrepArgs(self.X32.data_ptr(), self.XS, self.A0.data_ptr(), self.A0T.data_ptr(), ids.data_ptr(), self.nf,
                        dense.data_ptr(), self.nd, self.view("cache_emb").data_ptr(), self.view("cache_lin").data_ptr(),
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc, self.view("wd").data_ptr(),
                        self.view("bias").data_ptr(), self.S.data_ptr(), self.base.data_ptr(), B, self.K0p, self.Dp,
                        self.nf, self.ns, self.lin0, int(self.use_fm))
         _ck(lib.exb_prep(ctypes.byref(pa), B, self.Dp, st), "prep")
+        self._mark("prep")
         dims = [self.K0p] + self.Hp
         src = self.A0
         for l in range(L):
             G.gemm_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
                       ones_col=self.Hp[l] - 1, outT=self.HT[l] if l < L - 1 else None, stream=st)
             src = self.H[l]
+        self._mark("fwd_gemm")
         ha = _HeadArgs(self.H[-1].data_ptr(), self.Hp[-1], self.Hp[-1] - 1, self.view("wout").data_ptr(),
                        self.base.data_ptr(), labels.data_ptr(), self.dlogit.data_ptr(), self.loss.data_ptr(),
                        self.dZ[-1].data_ptr(), self.dZT[-1].data_ptr(), self.gview("wout").data_ptr(),
@@ -239,11 +258,21 @@ class FusedCTR:
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
                        self.gview("cache_lin").data_ptr(), B, 1.0 / B)
         _ck(lib.exb_head(ctypes.byref(ha), B, st), "head")
+        self._mark("head")
         for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
             G.gemm_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
                       ones_col=self.Hp[l - 1] - 1, outT=self.dZT[l - 1], mask=self.H[l - 1], stream=st)
         G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
                   S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
+        self._mark("dx_gemm")
+        forked = update and self.overlap
+        if forked:
+            cur = torch.cuda.current_stream(self.dev)
+            self._ev_fork.record(cur)
+            with torch.cuda.stream(self._s2):
+                self._s2.wait_event(self._ev_fork)
+                self.group.push_update(ids, self.G32)
+                self._ev_join.record(self._s2)
         for l in range(L):                 # dW_l = dZ_l^T @ H_{l-1}
             prevT = self.A0T if l == 0 else self.HT[l - 1]
             gW = self.gview("W%d" % l).view(self.Hp[l], dims[l])
@@ -252,20 +281,29 @@ class FusedCTR:
             _ck(lib.exb_cachegrad(self.G32.data_ptr(), self.XS, self.ns * self.Dp, self.Dp, ids.data_ptr(), self.nf,
                                   self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
                                   self.gview("cache_emb").data_ptr(), B, st), "cachegrad")
+        self._mark("dw_gemm+cachegrad")
         if update:
-            self.group.push_update(ids, self.G32)
-            if self._ar is not None:
-                self._ar()
-            _ck(lib.exb_adagrad_flat(self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr(), self.n_theta,
-                                     self.lr, self.eps, st), "adagrad")
+            if not forked:
+                self.group.push_update(ids, self.G32)
+                self._mark("push_update")
+            if self._ar is not None:     # all-reduce + Adagrad in one kernel
+                self._ar(self.theta, self.accum, self.lr, self.eps)
+                self._mark("allreduce+adagrad")
+            else:
+                _ck(lib.exb_adagrad_flat(self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr(),
+                                         self.n_theta, self.lr, self.eps, st), "adagrad")
             self.refresh_weights()
+            self._mark("adagrad+refresh")
+            if forked:
+                torch.cuda.current_stream(self.dev).wait_event(self._ev_join)
+                self._mark("join(push_update)")
         return self.loss.view(())
 
     def kernels_per_step(self):
         """launches of our own kernels in one training step"""
         L = len(self.hidden)
         n = 1 + 2 + L + 2 + L + L + (1 if self.nc else 0) + 1 + 1 + L   # pull prep(2) fwd head(2) dX dW cache push adagrad refresh
-        return n + (5 if self._ar is not None else 0)
+        return n     # world > 1: the fused all-reduce+Adagrad kernel replaces the Adagrad launch
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)
     def reference(self, ids, dense, labels):

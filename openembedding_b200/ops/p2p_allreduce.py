@@ -1,9 +1,9 @@
 """Two-shot all-reduce (sum) over peer-mapped gradient buffers -- NVLink P2P, no NCCL.
 
 Kernels: ``exb_ar_*`` in ``csrc/cuda/dense_kernels.cu``. Every rank owns a cudaMalloc'd
-gradient mirror and a flag block, both exported once with CUDA IPC; a call is five stream
-ordered launches (barrier, reduce-scatter by peer loads, barrier, all-gather by peer
-stores, barrier) plus two local copies, all graph-capturable.
+gradient buffer and a flag block, both exported once with CUDA IPC; a call is ONE persistent
+kernel (flag exchange, reduce-scatter by peer loads fused with the all-gather by peer stores,
+flag exchange, optional fused Adagrad), graph-capturable.
 """
 import ctypes
 
@@ -25,18 +25,26 @@ def tensor_from_ptr(ptr, numel, device, dtype=torch.float32):
 
 
 class P2PAllReduce:
-    def __init__(self, ctx, flat, ctas=64):
+    """``P2PAllReduce(ctx, n)`` owns the peer-mapped gradient buffer (``.grad``: write the
+    gradients there, no copies); ``P2PAllReduce(ctx, tensor)`` mirrors an existing flat
+    tensor through two local copies. ``__call__(theta, accum, lr, eps)`` fuses the dense
+    Adagrad step behind the reduction (one launch)."""
+
+    def __init__(self, ctx, flat, ctas=148):
         import torch.distributed as dist
-        assert flat.is_cuda and flat.dtype == torch.float32 and flat.numel() % 4 == 0
-        self.ctx, self.flat, self.W, self.rank = ctx, flat, ctx.world, ctx.rank
+        self.ctx, self.W, self.rank = ctx, ctx.world, ctx.rank
         self.lib = _native.cuda()
         from ..models import fused_dense
         fused_dense._lib()          # prototypes of the dense kernels
         eng = ctx.backend.engine
-        dev = flat.device
-        n = flat.numel()
-        per = ((n + self.W - 1) // self.W + 3) // 4 * 4
-        self.scratch = torch.empty(per, dtype=torch.float32, device=dev)
+        dev = ctx.device
+        if isinstance(flat, int):
+            n, self.flat = flat, None
+        else:
+            assert flat.is_cuda and flat.dtype == torch.float32
+            n, self.flat = flat.numel(), flat
+        assert n % 4 == 0
+        self.n, self.dev = n, dev
         self.ctas = ctas
         self.buf_ptr = self.lib.exb_raw_alloc(eng.device_index, n * 4)
         self.flag_ptr = self.lib.exb_raw_alloc(eng.device_index, 2 << 20)
@@ -52,19 +60,25 @@ class P2PAllReduce:
             else:
                 self.bufs[r], self.flags[r] = eng._open(bh), eng._open(fh)
         self.local = tensor_from_ptr(self.buf_ptr, n, dev)
+        self.grad = self.local
+        self.local.zero_()
         torch.cuda.synchronize(dev)
         dist.barrier(group=ctx.group)
 
-    def __call__(self):
-        st = torch.cuda.current_stream(self.flat.device).cuda_stream
-        self.local.copy_(self.flat, non_blocking=True)
-        # flag block: [0, 32) flags, epoch word at +1024, status word at +2048
-        rc = self.lib.exb_allreduce_sum(self.bufs, self.flags, self.flag_ptr + 1024, self.flag_ptr + 2048,
-                                        self.scratch.data_ptr(), self.flat.numel(), self.W, self.rank, self.ctas, st)
+    def __call__(self, theta=None, accum=None, lr=0.0, eps=0.0):
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.flat is not None:
+            self.local.copy_(self.flat, non_blocking=True)
+        # flag block: [0, 32) flags, epoch word at +1024, status word at +2048, CTA counter at +3072
+        rc = self.lib.exb_allreduce_adagrad(self.bufs, self.flags, self.flag_ptr + 1024, self.flag_ptr + 3072,
+                                            self.flag_ptr + 2048, self.n, self.W, self.rank, self.ctas,
+                                            theta.data_ptr() if theta is not None else 0,
+                                            accum.data_ptr() if accum is not None else 0, float(lr), float(eps), st)
         if rc != 0:
-            raise RuntimeError("exb_allreduce_sum: " + self.lib.exb_dense_last_error().decode())
-        self.flat.copy_(self.local, non_blocking=True)
+            raise RuntimeError("exb_allreduce_adagrad: " + self.lib.exb_dense_last_error().decode())
+        if self.flat is not None:
+            self.flat.copy_(self.local, non_blocking=True)
 
     def status(self):
-        t = tensor_from_ptr(self.flag_ptr + 2048, 1, self.flat.device, dtype=torch.int32)
+        t = tensor_from_ptr(self.flag_ptr + 2048, 1, self.dev, dtype=torch.int32)
         return int(t.item())

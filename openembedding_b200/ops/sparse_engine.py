@@ -308,6 +308,21 @@ class SparsePlan:
     def grid(self):
         return self.lib.exb_plan_grid(self.h, 0), self.lib.exb_plan_grid(self.h, 1)
 
+    TRACE_SLOTS = 32
+
+    def enable_trace(self, on=True):
+        """per-warp %globaltimer trace of the apply phase of push_update (tools/sparse_probe.py);
+        returns the int64 tensor [warps, TRACE_SLOTS]: slot 0 = phase start, then per task
+        8 slots: task id, t_count, t_ulist, t_cmap, t_resolved, t_gathered, t_done, -."""
+        if not on:
+            self.lib.exb_plan_set_trace(self.h, 0)
+            self._trace = None
+            return None
+        warps = self.grid()[1] * 8
+        self._trace = torch.zeros((warps, self.TRACE_SLOTS), dtype=torch.int64, device=self.e.device)
+        self.lib.exb_plan_set_trace(self.h, self._trace.data_ptr())
+        return self._trace
+
     def feature_slices(self):
         return [slice(o, o + d) for o, d in zip(self.feat_offsets, self.dims)]
 
