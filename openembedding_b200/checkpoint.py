@@ -53,6 +53,17 @@ def read_model_meta(path):
 
 
 def save_model(ctx, path, include_optimizer=True, num_files=None, persist=None):
+    """Collective. ``path`` may be a local directory, ``file://``, ``mem://null/`` (discard) or
+    ``hdfs://`` (every rank stages its shard files locally and uploads them, utils/fs.py)."""
+    from .utils.fs import Staging, URIConfig
+    cfg = URIConfig(path)
+    if cfg.is_null or cfg.is_local:
+        return _save_model_local(ctx, path if cfg.is_null else cfg.path, include_optimizer, num_files, persist)
+    with Staging(path, "w") as local:
+        return _save_model_local(ctx, local, include_optimizer, num_files, persist)
+
+
+def _save_model_local(ctx, path, include_optimizer=True, num_files=None, persist=None):
     """Collective. ``persist`` = dict(extra YAML keys) writes header-only records
     (num_items = 0), the lightweight host-tier checkpoint (EmbeddingDumpOperator.cpp:65-77)."""
     lib = _native.core()
@@ -153,6 +164,15 @@ def iter_shard_file(path):
 
 
 def load_model(ctx, path, restore_config_only=False):
+    from .utils.fs import Staging, URIConfig
+    cfg = URIConfig(path)
+    if cfg.is_local:
+        return _load_model_local(ctx, cfg.path, restore_config_only)
+    with Staging(path, "r") as local:
+        return _load_model_local(ctx, local, restore_config_only)
+
+
+def _load_model_local(ctx, path, restore_config_only=False):
     """Collective: every rank scans every file and keeps the rows it owns (re-shard)."""
     meta = read_model_meta(path)
     mine = model_meta_dict(ctx)["variables"]

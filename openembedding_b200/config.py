@@ -39,6 +39,48 @@ INITIALIZERS = {
 
 DTYPES = {"float32": 0x104, "float64": 0x108, "int8": 0x1, "int16": 0x2, "int32": 0x4, "int64": 0x8}
 DTYPE_NAMES = {v: k for k, v in DTYPES.items()}
+
+
+class DataType:
+    """dtype tag of a table (reference: openembedding/variable/DataType.h:20-134: the low byte of
+    the tag is the element size; only float32/float64 are registered for tables,
+    EmbeddingVariable.cpp:277-278). ``DataType("float32").size == 4``; ``int(dt)`` is the tag
+    stored in shard-file headers."""
+
+    def __init__(self, v):
+        if isinstance(v, DataType):
+            v = v.name
+        if isinstance(v, int):
+            if v not in DTYPE_NAMES:
+                raise ValueError("unknown datatype tag: %r" % v)
+            v = DTYPE_NAMES[v]
+        v = str(v).replace("torch.", "")
+        if v not in DTYPES:
+            raise ValueError("unknown datatype: %r" % v)
+        self.name, self.tag = v, DTYPES[v]
+
+    @property
+    def size(self):
+        return self.tag & 0xFF
+
+    @property
+    def is_table_type(self):
+        return self.name in ("float32", "float64")
+
+    def __int__(self):
+        return self.tag
+
+    def __str__(self):
+        return self.name
+
+    def __eq__(self, o):
+        try:
+            return self.tag == DataType(o).tag
+        except ValueError:
+            return False
+
+    def __hash__(self):
+        return hash(self.tag)
 HASH_KEY_RANGE = 2 ** 63
 
 

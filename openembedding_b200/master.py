@@ -218,3 +218,30 @@ class Server:
 
     def join(self):
         self._thread.join()
+
+
+def main(argv=None):
+    """``python -m openembedding_b200.master --bind_ip 0.0.0.0 --port 9090`` -- the standalone master
+    (reference: ``masterd``, pico-ps/pico-core/src/masterd.cc / openembedding/entry/masterd.cc)."""
+    import argparse
+    import signal
+    ap = argparse.ArgumentParser(prog="masterd")
+    ap.add_argument("--bind_ip", "--rpc_bind_ip", dest="bind_ip", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=0)
+    ap.add_argument("--endpoint", default="", help="ip:port (overrides --bind_ip/--port)")
+    a = ap.parse_args(argv)
+    ip, port = a.bind_ip, a.port
+    if a.endpoint:
+        ip, p = a.endpoint.rsplit(":", 1)
+        port = int(p)
+    m = Master(ip, port)
+    print("master endpoint %s" % m.endpoint, flush=True)
+    stop = threading.Event()
+    for sig in (signal.SIGINT, signal.SIGTERM):
+        signal.signal(sig, lambda *_: stop.set())
+    stop.wait()
+    m.finalize()
+
+
+if __name__ == "__main__":
+    main()

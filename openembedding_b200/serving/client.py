@@ -11,6 +11,7 @@ import itertools
 import json
 import time
 import urllib.request
+import zlib
 
 import numpy as np
 import torch
@@ -46,7 +47,10 @@ class ModelVariable:
 
 
 class ServingClient:
-    def __init__(self, master_endpoint, policy="round_robin"):
+    def __init__(self, master_endpoint, policy="round_robin", message_compress=""):
+        """message_compress: "" or "zlib" (EnvConfig server.message_compress; snappy/lz4 are accepted by the
+        config checker for compatibility but fall back to zlib, the only codec in the image)."""
+        self.compress = bool(message_compress)
         self.master = MasterClient(master_endpoint)
         self._rr = itertools.count()
         self.policy = policy
@@ -102,9 +106,16 @@ class ServingClient:
                 continue
             url = "http://%s/pull?model_sign=%s&variable_id=%d&shard_id=%d" % (nodes[nid], sign, vid, shard)
             try:
-                req = urllib.request.Request(url, data=local_ids.tobytes(), method="POST")
+                body, hdr = local_ids.tobytes(), {}
+                if self.compress:
+                    hdr["Accept-Encoding"] = "deflate"
+                    if len(body) >= 4096:
+                        body, hdr["Content-Encoding"] = zlib.compress(body, 1), "deflate"
+                req = urllib.request.Request(url, data=body, method="POST", headers=hdr)
                 with urllib.request.urlopen(req, timeout=max(0.5, timeout / 4)) as r:
                     data = r.read()
+                    if r.headers.get("Content-Encoding", "") == "deflate":
+                        data = zlib.decompress(data)
                 return np.frombuffer(data, dtype=np_dt).reshape(local_ids.size, dim)
             except Exception:
                 self._dead[nid] = time.time()         # handle_timeout: mark the node dead, retry elsewhere

@@ -12,6 +12,7 @@ import ctypes
 import json
 import os
 import threading
+import zlib
 import time
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 from urllib.parse import parse_qs, urlparse
@@ -67,6 +68,12 @@ class ServingNode:
                 if isinstance(body, (dict, list)):
                     body = json.dumps(body).encode()
                 self.send_response(code)
+                # server.message_compress (reference: RpcView compress, snappy/lz4/zlib): row payloads are
+                # deflated when the peer accepts it; only zlib is available in this image
+                if (ctype == "application/octet-stream" and len(body) >= 4096
+                        and "deflate" in self.headers.get("Accept-Encoding", "")):
+                    body = zlib.compress(body, 1)
+                    self.send_header("Content-Encoding", "deflate")
                 self.send_header("Content-Type", ctype)
                 self.send_header("Content-Length", str(len(body)))
                 self.end_headers()
@@ -74,7 +81,10 @@ class ServingNode:
 
             def _body(self):
                 n = int(self.headers.get("Content-Length", 0))
-                return self.rfile.read(n) if n else b""
+                data = self.rfile.read(n) if n else b""
+                if self.headers.get("Content-Encoding", "") == "deflate":
+                    data = zlib.decompress(data)
+                return data
 
             def do_GET(self):
                 u = urlparse(self.path)

@@ -1,0 +1,115 @@
+"""Status vocabulary, URI/file staging, DataType registry, message compression, masterd entry."""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from openembedding_b200.config import DataType
+from openembedding_b200.status import Status, StatusError, check, retry
+from openembedding_b200.utils.fs import Staging, URIConfig, exists
+
+
+def test_status_retry():
+    assert Status.OK.ok and Status.NO_REPLICA.retryable and not Status.FATAL.retryable
+    with pytest.raises(StatusError):
+        check(Status.INVALID_ID, "bad id")
+    calls = []
+
+    def flaky():
+        calls.append(1)
+        if len(calls) < 3:
+            raise StatusError(Status.TIMEOUT)
+        return 7
+    refreshed = []
+    assert retry(flaky, attempts=3, refresh=lambda: refreshed.append(1)) == 7 and len(refreshed) == 2
+    with pytest.raises(StatusError):
+        retry(lambda: check(Status.FATAL), attempts=3)
+
+
+def test_datatype():
+    dt = DataType("float32")
+    assert dt.size == 4 and int(dt) == 0x104 and dt.is_table_type and dt == "float32" and dt == 0x104
+    assert DataType(torch.float64).size == 8 and DataType(0x8).name == "int64" and not DataType("int8").is_table_type
+    with pytest.raises(ValueError):
+        DataType("float16")
+
+
+def test_uri_and_staging():
+    u = URIConfig("hdfs://nn/models/a?format=archive&x=1")
+    assert u.scheme == "hdfs" and u.path == "hdfs://nn/models/a" and u.params == {"format": "archive", "x": "1"}
+    assert URIConfig("/tmp/x").is_local and URIConfig("file:///tmp/x").path == "/tmp/x"
+    assert URIConfig("mem://null/").is_null
+    d = tempfile.mkdtemp()
+    with Staging(d + "/m", "w") as p:
+        open(os.path.join(p, "f"), "w").write("1")
+    assert exists(d + "/m/f")
+    with Staging("mem://null/", "w") as p:
+        open(os.path.join(p, "f"), "w").write("1")
+    assert not os.path.exists(p)
+
+
+def test_checkpoint_through_file_uri(cpu_context):
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    v = embed.Variable(shape=(100, 4), name="v", num_shards=1)
+    ctx = get_context()
+    ids = torch.arange(10)
+    v.push_gradients(ids, torch.ones(10, 4))
+    v.update_weights()
+    d = tempfile.mkdtemp()
+    checkpoint.save_model(ctx, "file://" + d + "/ck")
+    before = v.sparse_read(ids).clone()
+    v.push_gradients(ids, torch.ones(10, 4))
+    v.update_weights()
+    checkpoint.load_model(ctx, "file://" + d + "/ck")
+    assert torch.equal(v.sparse_read(ids), before)
+
+
+def test_serving_message_compress():
+    import openembedding_b200 as oe
+    import openembedding_b200.torch as embed
+    from openembedding_b200.context import reset_context
+    from openembedding_b200.serving.client import ServingClient
+    from openembedding_b200.serving.controller import ModelController
+    reset_context()
+    oe.flags.device = "cpu"
+    v = embed.Variable(shape=(5000, 8), name="v", num_shards=1,
+                       initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+    ids = torch.arange(3000)
+    ref = v.sparse_read(ids).clone()
+    v.push_gradients(ids, torch.zeros(3000, 8))
+    v.update_weights()
+    d = tempfile.mkdtemp()
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    checkpoint.save_model(get_context(), d + "/m", include_optimizer=False)
+    sign = get_context().model_sign()
+    master = oe.Master()
+    node = oe.Server(master_endpoint=master.endpoint)
+    ctl = ModelController(master.endpoint)
+    sign = ctl.create_model(d + "/m", replica_num=1, shard_num=1)
+    out_plain = ServingClient(master.endpoint).find_model_variable(sign, 0).pull(ids)
+    out_z = ServingClient(master.endpoint, message_compress="zlib").find_model_variable(sign, 0).pull(ids)
+    assert torch.allclose(out_plain, ref) and torch.equal(out_plain, out_z)
+    node.exit()
+    reset_context()
+
+
+def test_masterd_entry():
+    p = subprocess.Popen([sys.executable, "-m", "openembedding_b200.master", "--port", "0"], stdout=subprocess.PIPE,
+                         text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    try:
+        line = p.stdout.readline()
+        assert line.startswith("master endpoint ")
+        from openembedding_b200.master import MasterClient
+        c = MasterClient(line.split()[-1])
+        assert c.tree_node_add("x", "1") and c.tree_node_get("x") == "1" and c.generate_id("n") == 0
+    finally:
+        p.terminate()
+        p.wait(timeout=10)
