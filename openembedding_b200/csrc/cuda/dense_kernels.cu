@@ -13,7 +13,9 @@
 //             Horovod DistributedOptimizer (K5 in SURVEY 2.5)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include "pdl.cuh"
 #include <stdint.h>
+#include <string.h>
 
 #include <string>
 
@@ -31,12 +33,15 @@ struct PrepArgs {
     const float* wd; const float* bias;  // dense-linear weights [nd], global bias [1]
     float* S; float* base;               // [B, Dp], [B]
     int B, K0p, Dp, nf, ns, lin0, use_fm;   // lin0 = first column of the server linear terms in X32
+    float* loss;                         // [1] step loss accumulator, cleared here (head A adds to it)
 };
 
 // prep A: grid (B/32, ceil(K0p/256)); thread t owns ONE column of 32 batch rows: gathers cached
 //         rows / dense features / the ones column, writes A0 (row major) and A0T (batch major,
 //         64-byte runs). 7x more CTAs than a per-row-block loop: the kernel is latency bound.
 __global__ void __launch_bounds__(256) exb_prep_a_kernel(PrepArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     const int b0 = blockIdx.x * 32;
     const int col = blockIdx.y * 256 + threadIdx.x;
     if (col >= a.K0p) return;
@@ -94,8 +99,11 @@ __global__ void __launch_bounds__(256) exb_prep_a_kernel(PrepArgs a) {
 // prep B: one CTA per 8 batch rows: FM field sums with float4 loads (X32 is complete after
 //         prep A), linear terms, per-sample base logit
 __global__ void __launch_bounds__(256) exb_prep_b_kernel(PrepArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     __shared__ float sq[8], sfm[8], sl[8];
     const int b0 = blockIdx.x * 8;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss) *a.loss = 0.f;
     if (threadIdx.x < 8) { sq[threadIdx.x] = 0.f; sfm[threadIdx.x] = 0.f; sl[threadIdx.x] = 0.f; }
     __syncthreads();
     const int q4 = a.Dp / 4;
@@ -155,6 +163,8 @@ struct HeadArgs {
 
 // head A: one warp per batch row: logit, loss, dlogit; linear-term gradients of that row
 __global__ void __launch_bounds__(256) exb_head_a_kernel(HeadArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     __shared__ float s_loss[8], s_dl[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
@@ -205,6 +215,8 @@ __global__ void __launch_bounds__(256) exb_head_a_kernel(HeadArgs a) {
 // head B: grid (B/32, ceil(Hp/256)); thread = one column of 32 rows:
 //         dZ = dl * wout * relu'(H) in both layouts, g_wout
 __global__ void __launch_bounds__(256) exb_head_b_kernel(HeadArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     __shared__ float s_dl[32];
     const int b0 = blockIdx.x * 32;
     if (threadIdx.x < 32) s_dl[threadIdx.x] = (b0 + threadIdx.x < a.B) ? a.dlogit[b0 + threadIdx.x] : 0.f;
@@ -240,26 +252,150 @@ __global__ void __launch_bounds__(256) exb_head_b_kernel(HeadArgs a) {
     atomicAdd(&a.g_wout[n], gw);
 }
 
-// scatter-add the gradient rows of the cached (replicated) embedding tables
-__global__ void exb_cachegrad_kernel(const float* G32, long long xs, int col0, int Dp, const long long* ids, int ncols,
-                                     const int* cache_col, const long long* cache_off, int nc, float* g_cache_emb,
-                                     int B) {
-    const int chunks = Dp / 4;
-    const long long total = (long long)B * nc * chunks;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % chunks) * 4;
-        const int j = (int)((i / chunks) % nc);
-        const int b = (int)(i / ((long long)chunks * nc));
-        const float4 g = *reinterpret_cast<const float4*>(G32 + (size_t)b * xs + col0 + j * Dp + c);
-        const long long id = ids[(size_t)b * ncols + cache_col[j]];
-        float* dst = g_cache_emb + (size_t)(cache_off[j] + id) * Dp + c;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+// Scatter-add the gradient rows of the cached (replicated) embedding tables.
+// One warp per (32 batch rows, cached feature): the 32 gradient rows go through a per-warp
+// shared-memory tile, rows with the SAME id are summed there (__match_any_sync groups), and one
+// red.global.add.v4 per (distinct id, 4 columns) leaves the warp. Cached tables are the
+// small-vocabulary ones (3..4096 rows), so a batch hits each row up to thousands of times; the
+// first version issued one global atomic per (sample, 4 columns) and serialised on those rows.
+#define EXB_CG_MAXDP 128
+__global__ void __launch_bounds__(256) exb_cachegrad_kernel(const float* G32, long long xs, int col0, int Dp,
+                                                            const long long* ids, int ncols, const int* cache_col,
+                                                            const long long* cache_off, int nc, float* g_cache_emb,
+                                                            int B) {
+    exb::pdl_trigger();
+    extern __shared__ __align__(16) float cg_smem[];
+    exb::pdl_wait();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    float* tile = cg_smem + (size_t)wic * 32 * Dp;
+    const int chunks = Dp >> 2;
+    const int ntask = ((B + 31) / 32) * nc;
+    for (int task = warp; task < ntask; task += nwarps) {
+        const int j = task % nc, b0 = (task / nc) * 32;
+        const int b = b0 + lane;
+        const long long id = (b < B) ? ids[(size_t)b * ncols + cache_col[j]] : -1ll - lane;
+        const float* src = G32 + (size_t)b0 * xs + col0 + j * Dp;
+        for (int idx = lane; idx < 32 * chunks; idx += 32) {       // coalesced: consecutive lanes, consecutive float4
+            const int r = idx / chunks, c = idx - r * chunks;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + r < B) v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * xs) + c);
+            reinterpret_cast<float4*>(tile)[idx] = v;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, id);
+        unsigned leaders = __ballot_sync(0xffffffffu, b < B && lane == __ffs(grp) - 1);
+        __syncwarp();
+        const long long base = cache_off[j];
+        while (leaders) {                                           // warp-uniform
+            const int L = __ffs(leaders) - 1;
+            leaders &= leaders - 1;
+            const unsigned members = __shfl_sync(0xffffffffu, grp, L);
+            const long long lid = __shfl_sync(0xffffffffu, id, L);
+            float* dst = g_cache_emb + (size_t)(base + lid) * Dp;
+            for (int c = lane; c < chunks; c += 32) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (unsigned m = members; m; m &= m - 1) {
+                    const float4 v = reinterpret_cast<const float4*>(tile)[(__ffs(m) - 1) * chunks + c];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 4), "f"(acc.x), "f"(acc.y),
+                             "f"(acc.z), "f"(acc.w) : "memory");
+            }
+        }
+        __syncwarp();
     }
+}
+
+// ---- dense optimizer step: Adagrad + bf16 weight refresh + gradient clearing in ONE pass ----
+// theta is the flat fp32 parameter buffer; the first `nmat` segments are the MLP weight matrices
+// [R, C] whose bf16 copy Wb [R, C] and transposed copy WTb [C, R] feed the tcgen05 GEMMs of the
+// next step. A 256-thread CTA (32x8) walks 32x32 tiles: read g/accum/w once, write w/accum, the
+// bf16 tile, the transposed bf16 tile (through shared memory) and zero the gradient, so the
+// step needs no separate memset / Adagrad / 3x refresh launches. Elements outside the matrices
+// (output weights, dense-linear weights, bias, cached embedding tables) are updated flat.
+struct OptMat { long long off; int R, C; __nv_bfloat16* Wb; __nv_bfloat16* WTb; };
+struct DenseOptArgs {
+    float* theta; float* accum; float* grad;
+    long long n, flat_lo;          // [flat_lo, n) is the flat region (matrices come first)
+    float lr, eps;
+    int nmat, zero_grad;
+    OptMat mat[4];
+};
+
+__device__ __forceinline__ float adagrad_one(float& w, float& a, float g, float lr, float eps) {
+    a += g * g;
+    w -= lr * g / (sqrtf(a) + eps);
+    return w;
+}
+
+__device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*tile)[33]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // launched with 256 threads
+    int tile_base = 0;
+    for (int mi = 0; mi < o.nmat; ++mi) {
+        const OptMat M = o.mat[mi];
+        const int tc = (M.C + 31) / 32, tr = (M.R + 31) / 32, nt = tc * tr;
+        // tiles of all matrices form one global list; CTA b takes tiles b, b+grid, ...
+        const int G = (int)gridDim.x;
+        for (int t = ((int)blockIdx.x - tile_base % G + G) % G; t < nt; t += G) {
+            const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+            for (int i = ty; i < 32; i += 8) {
+                const int r = r0 + i, c = c0 + tx;
+                float w = 0.f;
+                if (r < M.R && c < M.C) {
+                    const long long k = M.off + (long long)r * M.C + c;
+                    const float g = __ldcg(o.grad + k);
+                    float a = o.accum[k];
+                    w = o.theta[k];
+                    adagrad_one(w, a, g, o.lr, o.eps);
+                    o.accum[k] = a;
+                    o.theta[k] = w;
+                    if (o.zero_grad) o.grad[k] = 0.f;
+                    M.Wb[(size_t)r * M.C + c] = __float2bfloat16_rn(w);
+                }
+                tile[i][tx] = w;
+            }
+            __syncthreads();
+            for (int i = ty; i < 32; i += 8) {
+                const int c = c0 + i, r = r0 + tx;
+                if (r < M.R && c < M.C) M.WTb[(size_t)c * M.R + r] = __float2bfloat16_rn(tile[tx][i]);
+            }
+            __syncthreads();
+        }
+        tile_base += nt;
+    }
+    for (long long i = o.flat_lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < o.n;
+         i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < o.n) {
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(o.grad + i));
+            float4 a = *reinterpret_cast<float4*>(o.accum + i);
+            float4 w = *reinterpret_cast<float4*>(o.theta + i);
+            adagrad_one(w.x, a.x, g.x, o.lr, o.eps); adagrad_one(w.y, a.y, g.y, o.lr, o.eps);
+            adagrad_one(w.z, a.z, g.z, o.lr, o.eps); adagrad_one(w.w, a.w, g.w, o.lr, o.eps);
+            *reinterpret_cast<float4*>(o.accum + i) = a;
+            *reinterpret_cast<float4*>(o.theta + i) = w;
+            if (o.zero_grad) *reinterpret_cast<float4*>(o.grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (long long k = i; k < o.n; ++k) {
+                float a = o.accum[k], w = o.theta[k];
+                adagrad_one(w, a, o.grad[k], o.lr, o.eps);
+                o.accum[k] = a; o.theta[k] = w;
+                if (o.zero_grad) o.grad[k] = 0.f;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) exb_dense_opt_kernel(DenseOptArgs o) {
+    __shared__ float tile[32][33];
+    exb::pdl_trigger();
+    exb::pdl_wait();
+    dense_opt_step(o, tile);
 }
 
 // Adagrad on the flat fp32 buffer (tf.keras semantics: accum += g^2; w -= lr * g / (sqrt(accum) + eps))
 __global__ void exb_adagrad_flat_kernel(float* theta, float* accum, const float* grad, long long n, float lr, float eps) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < n;
          i += (long long)gridDim.x * blockDim.x * 4) {
         if (i + 3 < n) {
@@ -283,6 +419,8 @@ __global__ void exb_adagrad_flat_kernel(float* theta, float* accum, const float*
 
 // W fp32 [R, C] -> Wb bf16 [R, C] and WTb bf16 [C, R] (32x32 smem tile transpose)
 __global__ void exb_refresh_bf16_kernel(const float* W, __nv_bfloat16* Wb, __nv_bfloat16* WTb, int R, int C) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     __shared__ float tile[32][33];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -342,8 +480,11 @@ __device__ __forceinline__ void ar_wait(const ArArgs& a, unsigned e) {     // ev
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, float* theta, float* accum, float lr, float eps) {
+__global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, DenseOptArgs o) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
     __shared__ int s_last;
+    __shared__ float opt_tile[32][33];
     const unsigned e0 = *(volatile unsigned*)a.epoch;
     if (blockIdx.x == 0) ar_signal(a, e0 + 1);     // earlier kernels of this stream wrote the gradients
     ar_wait(a, e0 + 1);
@@ -379,19 +520,8 @@ __global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, float* thet
         ar_signal(a, e0 + 2);
     }
     ar_wait(a, e0 + 2);
-    if (theta == nullptr) return;
-    const float* grad = a.buf[a.rank];
-    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < a.n;
-         i += (long long)gridDim.x * blockDim.x * 4) {
-        float4 g = __ldcg(reinterpret_cast<const float4*>(grad + i));
-        float4 ac = *reinterpret_cast<float4*>(accum + i);
-        float4 w = *reinterpret_cast<float4*>(theta + i);
-        ac.x += g.x * g.x; ac.y += g.y * g.y; ac.z += g.z * g.z; ac.w += g.w * g.w;
-        w.x -= lr * g.x / (sqrtf(ac.x) + eps); w.y -= lr * g.y / (sqrtf(ac.y) + eps);
-        w.z -= lr * g.z / (sqrtf(ac.z) + eps); w.w -= lr * g.w / (sqrtf(ac.w) + eps);
-        *reinterpret_cast<float4*>(accum + i) = ac;
-        *reinterpret_cast<float4*>(theta + i) = w;
-    }
+    if (o.theta == nullptr) return;
+    dense_opt_step(o, opt_tile);     // o.grad == a.buf[a.rank]: identical on every rank now
 }
 
 }  // namespace
@@ -404,19 +534,17 @@ int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
     PrepArgs a = *reinterpret_cast<const PrepArgs*>(args);
     (void)Dp;
     dim3 ga((B + 31) / 32, (a.K0p + 255) / 256);
-    exb_prep_a_kernel<<<ga, 256, 0, (cudaStream_t)stream>>>(a);
-    exb_prep_b_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = exb::launch_pdl(exb_prep_a_kernel, ga, dim3(256), 0, (cudaStream_t)stream, a);
+    if (e == cudaSuccess) e = exb::launch_pdl(exb_prep_b_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
 int exb_prep_args_size() { return (int)sizeof(PrepArgs); }
 int exb_head(const void* args, int B, uint64_t stream) {
     HeadArgs a = *reinterpret_cast<const HeadArgs*>(args);
-    exb_head_a_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = exb::launch_pdl(exb_head_a_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
     dim3 gb((B + 31) / 32, (a.Hp + 255) / 256);
-    exb_head_b_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = exb::launch_pdl(exb_head_b_kernel, gb, dim3(256), 0, (cudaStream_t)stream, a);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
@@ -424,13 +552,16 @@ int exb_head_args_size() { return (int)sizeof(HeadArgs); }
 int exb_cachegrad(uint64_t G32, long long xs, int col0, int Dp, uint64_t ids, int ncols, uint64_t cache_col,
                   uint64_t cache_off, int nc, uint64_t g_cache_emb, int B, uint64_t stream) {
     if (nc == 0) return 0;
-    long long total = (long long)B * nc * (Dp / 4);
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 8) grid = 148 * 8;
-    exb_cachegrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)G32, xs, col0, Dp, (const long long*)ids,
-                                                                 ncols, (const int*)cache_col, (const long long*)cache_off,
-                                                                 nc, (float*)g_cache_emb, B);
-    cudaError_t e = cudaGetLastError();
+    if (Dp % 4 || Dp > EXB_CG_MAXDP) { g_dense_err = "cachegrad: Dp must be a multiple of 4 and <= 128"; return -1; }
+    const int ntask = ((B + 31) / 32) * nc;
+    int grid = (ntask + 7) / 8;
+    if (grid > 148 * 4) grid = 148 * 4;
+    const size_t smem = (size_t)8 * 32 * Dp * sizeof(float);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(exb_cachegrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * EXB_CG_MAXDP * 4); attr = true; }
+    cudaError_t e = exb::launch_pdl(exb_cachegrad_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const float*)G32,
+                                    xs, col0, Dp, (const long long*)ids, ncols, (const int*)cache_col,
+                                    (const long long*)cache_off, nc, (float*)g_cache_emb, B);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
@@ -438,38 +569,49 @@ int exb_adagrad_flat(uint64_t theta, uint64_t accum, uint64_t grad, long long n,
     int grid = (int)((n / 4 + 255) / 256);
     if (grid > 148 * 4) grid = 148 * 4;
     if (grid < 1) grid = 1;
-    exb_adagrad_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)theta, (float*)accum, (const float*)grad, n, lr, eps);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = exb::launch_pdl(exb_adagrad_flat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (float*)theta,
+                                    (float*)accum, (const float*)grad, n, lr, eps);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
 int exb_refresh_bf16(uint64_t W, uint64_t Wb, uint64_t WTb, int R, int C, uint64_t stream) {
     dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-    exb_refresh_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float*)W, (__nv_bfloat16*)Wb, (__nv_bfloat16*)WTb, R, C);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = exb::launch_pdl(exb_refresh_bf16_kernel, grid, block, 0, (cudaStream_t)stream, (const float*)W,
+                                    (__nv_bfloat16*)Wb, (__nv_bfloat16*)WTb, R, C);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
+// Adagrad + bf16 refresh + gradient clearing of the whole dense parameter buffer in one launch
+int exb_dense_opt(const void* args, uint64_t stream) {
+    DenseOptArgs o = *reinterpret_cast<const DenseOptArgs*>(args);
+    int tiles = 0;
+    for (int i = 0; i < o.nmat; ++i) tiles += ((o.mat[i].R + 31) / 32) * ((o.mat[i].C + 31) / 32);
+    int grid = tiles > 0 ? tiles : 1;
+    if (grid > 148 * 8) grid = 148 * 8;
+    cudaError_t e = exb::launch_pdl(exb_dense_opt_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, o);
+    if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+int exb_dense_opt_args_size() { return (int)sizeof(DenseOptArgs); }
 
 // all-reduce (sum, in place) of a flat fp32 buffer of n elements (n % 4 == 0, 16-byte aligned)
 // that every rank has peer-mapped; bufs/flags: W pointers each; epoch/gcount/status: local words.
 // theta/accum != 0: Adagrad step on the reduced gradient inside the same kernel.
 int exb_allreduce_adagrad(const uint64_t* bufs, const uint64_t* flags, uint64_t epoch, uint64_t gcount, uint64_t status,
-                          long long n, int W, int rank, int ctas, uint64_t theta, uint64_t accum, float lr, float eps,
-                          uint64_t stream) {
+                          long long n, int W, int rank, int ctas, const void* opt_args, uint64_t stream) {
     ArArgs a;
     for (int i = 0; i < 8; ++i) { a.buf[i] = i < W ? (float*)bufs[i] : nullptr; a.flags[i] = i < W ? (unsigned*)flags[i] : nullptr; }
     a.epoch = (unsigned*)epoch; a.gcount = (unsigned*)gcount; a.status = (int*)status; a.n = n; a.W = W; a.rank = rank;
     if (n % 4) { g_dense_err = "allreduce: n must be a multiple of 4"; return -1; }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_ar_fused_kernel, 256, 0);
+    DenseOptArgs o;
+    memset(&o, 0, sizeof(o));
+    if (opt_args) o = *reinterpret_cast<const DenseOptArgs*>(opt_args);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (ctas < 1) ctas = 1;
     if (ctas > sms) ctas = sms;             // CTAs wait on each other: keep the grid resident
-    exb_ar_fused_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(a, (float*)theta, (float*)accum, lr, eps);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = exb::launch_pdl(exb_ar_fused_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, a, o);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }

@@ -762,18 +762,16 @@ int exb_pull(void* ph, uint64_t ids, uint64_t out, int n_rows, uint64_t stream) 
     Plan* p = (Plan*)ph;
     Engine* e = p->e;
     if (n_rows > p->d.B) return fail_msg("pull: n_rows exceeds plan batch");
-    exb_pull_kernel<<<p->grid_pull, 256, p->smem_pull, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
-                                                                    (float*)out, n_rows);
-    CK(cudaGetLastError());
+    CK(launch_pdl(exb_pull_kernel, dim3(p->grid_pull), dim3(256), p->smem_pull, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const long long*)ids, (float*)out, n_rows));
     return 0;
 }
 int exb_push_update(void* ph, uint64_t ids, uint64_t grads, int n_rows, uint64_t stream) {
     Plan* p = (Plan*)ph;
     Engine* e = p->e;
     if (n_rows > p->d.B) return fail_msg("push: n_rows exceeds plan batch");
-    exb_push_update_kernel<<<p->grid_push, 256, p->smem_push, (cudaStream_t)stream>>>(e->d_tables, p->d, (const long long*)ids,
-                                                                           (const float*)grads, n_rows);
-    CK(cudaGetLastError());
+    CK(launch_pdl(exb_push_update_kernel, dim3(p->grid_push), dim3(256), p->smem_push, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const long long*)ids, (const float*)grads, n_rows));
     return 0;
 }
 

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include "pdl.cuh"
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -119,6 +120,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+    exb::pdl_trigger();   // the next kernel of the step may be scheduled once all CTAs are resident
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, n_blk = blockIdx.y;
     const bool dbg = E.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -143,6 +145,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    exb::pdl_wait();      // barriers, TMEM and tensor maps are ready; operands come from the previous kernel
     if (threadIdx.x == 0) GSTAMP(1);
 
     if (warp == 0) {
@@ -390,8 +393,9 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    exb_gemm_tcgen05_kernel<64><<<grid, NUM_THREADS, gemm_smem<64>(), (cudaStream_t)stream>>>(tmA, tmB, tmO, tmT, E, nkb, per);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = exb::launch_pdl(exb_gemm_tcgen05_kernel<64>, grid, dim3(NUM_THREADS), gemm_smem<64>(),
+                                      (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(err); return -1; }
     return 0;
 }

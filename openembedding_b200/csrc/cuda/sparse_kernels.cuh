@@ -25,6 +25,7 @@
 // summed (MpscGradientReducer.h:30-53); rows are materialised at their first update.
 #pragma once
 #include "exb_common.cuh"
+#include "pdl.cuh"
 #include "bulk_rows.cuh"
 
 namespace exb {
@@ -183,7 +184,9 @@ __global__ void __launch_bounds__(256, 3)
 exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long* __restrict__ ids,
                 float* __restrict__ out, int n_rows) {
     extern __shared__ __align__(16) unsigned char exb_smem[];
-    const SmemView S = stage_plan(tables, P, exb_smem);
+    pdl_trigger();
+    const SmemView S = stage_plan(tables, P, exb_smem);   // descriptors are written by the host only
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -522,7 +525,9 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                        const long long* __restrict__ ids, const float* __restrict__ grads,
                        int n_rows) {
     extern __shared__ __align__(16) unsigned char exb_smem[];
+    pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
+    pdl_wait();
     int* s_prefix = S.seg_prefix;
     const int wic = threadIdx.x >> 5;
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, true);

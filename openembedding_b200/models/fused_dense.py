@@ -35,7 +35,8 @@ class _PrepArgs(ctypes.Structure):
                 ("ncols", c_int), ("dense", c_void_p), ("nd", c_int), ("cache_emb", c_void_p),
                 ("cache_lin", c_void_p), ("cache_col", c_void_p), ("cache_off", c_void_p), ("nc", c_int),
                 ("wd", c_void_p), ("bias", c_void_p), ("S", c_void_p), ("base", c_void_p), ("B", c_int),
-                ("K0p", c_int), ("Dp", c_int), ("nf", c_int), ("ns", c_int), ("lin0", c_int), ("use_fm", c_int)]
+                ("K0p", c_int), ("Dp", c_int), ("nf", c_int), ("ns", c_int), ("lin0", c_int), ("use_fm", c_int),
+                ("loss", c_void_p)]
 
 
 class _HeadArgs(ctypes.Structure):
@@ -45,6 +46,15 @@ class _HeadArgs(ctypes.Structure):
                 ("G32", c_void_p), ("xs", c_longlong), ("lin0", c_int), ("ns", c_int), ("ids", c_void_p),
                 ("ncols", c_int), ("cache_col", c_void_p), ("cache_off", c_void_p), ("nc", c_int),
                 ("g_cache_lin", c_void_p), ("B", c_int), ("grad_scale", c_float)]
+
+
+class _OptMat(ctypes.Structure):
+    _fields_ = [("off", c_longlong), ("R", c_int), ("C", c_int), ("Wb", c_void_p), ("WTb", c_void_p)]
+
+
+class _DenseOptArgs(ctypes.Structure):
+    _fields_ = [("theta", c_void_p), ("accum", c_void_p), ("grad", c_void_p), ("n", c_longlong), ("flat_lo", c_longlong),
+                ("lr", c_float), ("eps", c_float), ("nmat", c_int), ("zero_grad", c_int), ("mat", _OptMat * 4)]
 
 
 def _r(x, m):
@@ -73,7 +83,10 @@ def _lib():
         lib.exb_refresh_bf16.argtypes = [u64, u64, u64, c_int, c_int, u64]
         lib.exb_allreduce_adagrad.restype = c_int
         lib.exb_allreduce_adagrad.argtypes = [ctypes.POINTER(u64), ctypes.POINTER(u64), u64, u64, u64, c_longlong, c_int,
-                                              c_int, c_int, u64, u64, c_float, c_float, u64]
+                                              c_int, c_int, c_void_p, u64]
+        lib.exb_dense_opt.restype = c_int
+        lib.exb_dense_opt.argtypes = [c_void_p, u64]
+        assert lib.exb_dense_opt_args_size() == ctypes.sizeof(_DenseOptArgs), "DenseOptArgs ABI mismatch"
         lib.exb_dense_last_error.restype = ctypes.c_char_p
         assert lib.exb_prep_args_size() == ctypes.sizeof(_PrepArgs), "PrepArgs ABI mismatch"
         assert lib.exb_head_args_size() == ctypes.sizeof(_HeadArgs), "HeadArgs ABI mismatch"
@@ -195,9 +208,19 @@ class FusedCTR:
         self.cache_col = torch.tensor(self.cached or [0], dtype=torch.int32, device=dev)
         self.cache_off = torch.tensor(offs_c or [0], dtype=torch.int64, device=dev)
         # push+update runs on a second stream next to the dW GEMMs / dense optimizer (fork after dX1, join at step end)
-        self.overlap = os.environ.get("EXB_OVERLAP", "1") != "0"
+        self.overlap = os.environ.get("EXB_OVERLAP", "0") == "1"
         self._s2 = torch.cuda.Stream(device=dev)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        assert L <= 4, "the fused optimizer kernel takes at most 4 weight matrices"
+        oa = _DenseOptArgs()
+        oa.theta, oa.accum, oa.grad = self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr()
+        oa.n, oa.flat_lo, oa.lr, oa.eps = self.n_theta, segs["wout"][0], self.lr, self.eps
+        oa.nmat, oa.zero_grad = L, 1
+        for l in range(L):
+            oa.mat[l].off, oa.mat[l].R, oa.mat[l].C = segs["W%d" % l][0], self.Hp[l], dims[l]
+            oa.mat[l].Wb, oa.mat[l].WTb = self.Wb[l].data_ptr(), self.WTb[l].data_ptr()
+        self._opt_args = oa
+        self._grad_dirty = False
         self.refresh_weights()
         torch.cuda.synchronize(dev)
 
@@ -231,8 +254,9 @@ class FusedCTR:
     def forward_backward(self, ids, dense, labels, update=True):
         B, L, lib, st = self.B, len(self.hidden), self.lib, self._st()
         assert ids.shape == (B, self.nf) and ids.dtype == torch.int64 and ids.is_contiguous()
-        self.gtheta.zero_()
-        self.loss.zero_()
+        if self._grad_dirty:          # the optimizer kernel clears the gradients it consumed; a call with
+            self.gtheta.zero_()       # update=False leaves them behind
+            self._grad_dirty = False
         self._mark("start")
         self.group.pull(ids, out=self.X32)
         self._mark("pull")
@@ -240,7 +264,7 @@ class FusedCTR:
                        dense.data_ptr(), self.nd, self.view("cache_emb").data_ptr(), self.view("cache_lin").data_ptr(),
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc, self.view("wd").data_ptr(),
                        self.view("bias").data_ptr(), self.S.data_ptr(), self.base.data_ptr(), B, self.K0p, self.Dp,
-                       self.nf, self.ns, self.lin0, int(self.use_fm))
+                       self.nf, self.ns, self.lin0, int(self.use_fm), self.loss.data_ptr())
         _ck(lib.exb_prep(ctypes.byref(pa), B, self.Dp, st), "prep")
         self._mark("prep")
         dims = [self.K0p] + self.Hp
@@ -286,23 +310,25 @@ class FusedCTR:
             if not forked:
                 self.group.push_update(ids, self.G32)
                 self._mark("push_update")
-            if self._ar is not None:     # all-reduce + Adagrad in one kernel
-                self._ar(self.theta, self.accum, self.lr, self.eps)
-                self._mark("allreduce+adagrad")
+            # Adagrad + bf16 weight refresh + gradient clearing: one kernel (world > 1: behind the all-reduce,
+            # in the same kernel)
+            if self._ar is not None:
+                self._ar(self._opt_args)
+                self._mark("allreduce+optimizer")
             else:
-                _ck(lib.exb_adagrad_flat(self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr(),
-                                         self.n_theta, self.lr, self.eps, st), "adagrad")
-            self.refresh_weights()
-            self._mark("adagrad+refresh")
+                _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
+            self._mark("optimizer")
             if forked:
                 torch.cuda.current_stream(self.dev).wait_event(self._ev_join)
                 self._mark("join(push_update)")
+        else:
+            self._grad_dirty = True
         return self.loss.view(())
 
     def kernels_per_step(self):
         """launches of our own kernels in one training step"""
         L = len(self.hidden)
-        n = 1 + 2 + L + 2 + L + L + (1 if self.nc else 0) + 1 + 1 + L   # pull prep(2) fwd head(2) dX dW cache push adagrad refresh
+        n = 1 + 2 + L + 2 + L + L + (1 if self.nc else 0) + 1 + 1   # pull prep(2) fwd head(2) dX dW cache push optimizer
         return n     # world > 1: the fused all-reduce+Adagrad kernel replaces the Adagrad launch
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)

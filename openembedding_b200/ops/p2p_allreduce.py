@@ -65,15 +65,16 @@ class P2PAllReduce:
         torch.cuda.synchronize(dev)
         dist.barrier(group=ctx.group)
 
-    def __call__(self, theta=None, accum=None, lr=0.0, eps=0.0):
+    def __call__(self, opt_args=None):
+        """opt_args: a ``models.fused_dense._DenseOptArgs`` whose ``grad`` is ``self.grad`` -- the dense
+        optimizer step then runs inside the same kernel, behind the reduction."""
         st = torch.cuda.current_stream(self.dev).cuda_stream
         if self.flat is not None:
             self.local.copy_(self.flat, non_blocking=True)
         # flag block: [0, 32) flags, epoch word at +1024, status word at +2048, CTA counter at +3072
         rc = self.lib.exb_allreduce_adagrad(self.bufs, self.flags, self.flag_ptr + 1024, self.flag_ptr + 3072,
                                             self.flag_ptr + 2048, self.n, self.W, self.rank, self.ctas,
-                                            theta.data_ptr() if theta is not None else 0,
-                                            accum.data_ptr() if accum is not None else 0, float(lr), float(eps), st)
+                                            ctypes.byref(opt_args) if opt_args is not None else None, st)
         if rc != 0:
             raise RuntimeError("exb_allreduce_adagrad: " + self.lib.exb_dense_last_error().decode())
         if self.flat is not None:
