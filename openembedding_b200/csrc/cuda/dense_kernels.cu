@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) exb_prep_a_kernel(PrepArgs a) {
         pk[r >> 1] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h0)) |
                      ((uint32_t)(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
     }
+    if (a.A0T == nullptr) return;   // dW GEMMs read A0 itself as an MN-major operand
     if (full) {
         uint4* tp = reinterpret_cast<uint4*>(a.A0T + (size_t)col * a.B + b0);
 #pragma unroll
@@ -239,7 +240,8 @@ __global__ void __launch_bounds__(256) exb_head_b_kernel(HeadArgs a) {
         const uint16_t u = *reinterpret_cast<const uint16_t*>(&hb);
         if (r & 1) pk[r >> 1] |= (uint32_t)u << 16; else pk[r >> 1] = u;
     }
-    if (b0 + 31 < a.B) {
+    if (a.dZT == nullptr) {
+    } else if (b0 + 31 < a.B) {
         uint4* tp = reinterpret_cast<uint4*>(a.dZT + (size_t)n * a.B + b0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tp[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);

@@ -26,6 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <string>
 
@@ -41,7 +42,7 @@ enum EpiMode : int { EPI_FWD = 0, EPI_DX = 1, EPI_DW = 2, EPI_DX_FM = 3 };
 
 struct GemmEpi {
     int mode, relu, ones_col, fm_cols;
-    int M, N, D, _pad;
+    int M, N, D, mn_major;   // mn_major: A is stored [K, M], B is stored [K, N] (MN contiguous)
     void* out; long long ldo;
     __nv_bfloat16* outT; long long ldoT;
     const __nv_bfloat16* mask; long long ldmask;
@@ -81,6 +82,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
     d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// MN-major, SWIZZLE_128B: the tile is [k rows][64 MN elements = 128 B]; 8 k-rows form a 1024-byte
+// swizzle atom (stride byte offset), 64-element MN blocks are `lbo_bytes` apart (leading byte
+// offset). Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -155,6 +168,12 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                if (E.mn_major) {   // boxes of 64 MN elements x 64 k rows; the A tile is two MN blocks
+                    tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], m_blk * BM, (kb0 + i) * BK);
+                    tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], m_blk * BM + 64, (kb0 + i) * BK);
+                    tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], n_blk * BN, (kb0 + i) * BK);
+                    continue;
+                }
                 tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + i) * BK, m_blk * BM);
                 tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], (kb0 + i) * BK, n_blk * BN);
             }
@@ -170,9 +189,18 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (i == 0) GSTAMP(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+                if (E.mn_major) {
+                    // both operands MN-major (bits 15/16); one UMMA_K = 16 k rows = two swizzle atoms = 2048 B
+                    const uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_base, umma_desc_mn(a0 + k * 2048, A_BYTES / 2), umma_desc_mn(b0 + k * 2048, B_BYTES),
+                                  idesc_mn, (i | k) ? 1u : 0u);
+                } else {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128B swizzle row
                     umma_bf16(tmem_base, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc, (i | k) ? 1u : 0u);
+                }
                 umma_commit(&empty[s]);            // smem stage reusable when these MMAs retire
             }
             umma_commit(tmem_full);                // accumulator complete
@@ -377,7 +405,7 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     tmT = tmO;
     if (outT && !make_map_ex(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)outT, (N + 63) / 64 * 64, M, ldoT, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     GemmEpi E;
-    E.mode = mode; E.relu = relu; E.ones_col = ones_col; E.fm_cols = fm_cols; E.M = M; E.N = N; E.D = D > 0 ? D : 1; E._pad = 0;
+    E.mode = mode; E.relu = relu; E.ones_col = ones_col; E.fm_cols = fm_cols; E.M = M; E.N = N; E.D = D > 0 ? D : 1; E.mn_major = 0;
     E.out = (void*)out; E.ldo = ldo; E.outT = (__nv_bfloat16*)outT; E.ldoT = ldoT;
     E.mask = (const __nv_bfloat16*)mask; E.ldmask = ldmask;
     E.dlogit = (const float*)dlogit; E.S = (const float*)S; E.emb = (const float*)emb; E.ldemb = ldemb;
@@ -397,6 +425,40 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
                                       (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(err); return -1; }
+    return 0;
+}
+
+// dW-style product from batch-major operands, no transposed copies needed:
+//   out[M, N] (fp32, += via TMA reduce-add) = A[K, M]^T * B[K, N],  A/B bf16 row-major with K rows
+// (e.g. M = features of dZ, N = features of the layer input, K = batch). M, N: any; K % 64 == 0;
+// lda/ldb multiples of 8 elements. Both operands reach the tensor core as MN-major tiles.
+int exb_gemm_bf16_tn(uint64_t A, long long lda, uint64_t B, long long ldb, int M, int N, int K, uint64_t out,
+                     long long ldo, int splits, uint64_t stream) {
+    if (K % BK != 0 || lda % 8 != 0 || ldb % 8 != 0) { g_gemm_err = "gemm_tn: K %% 64 / ld %% 8 violated"; return -1; }
+    CUtensorMap tmA, tmB, tmO, tmT;
+    if (!make_map_ex(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)A, K, M, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (!make_map_ex(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)B, K, N, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (!make_map_ex(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (const void*)out, M, N, ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    tmT = tmO;
+    GemmEpi E;
+    memset(&E, 0, sizeof(E));
+    E.mode = EPI_DW; E.ones_col = -1; E.M = M; E.N = N; E.D = 1; E.mn_major = 1;
+    E.out = (void*)out; E.ldo = ldo;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
+        attr_set = true;
+    }
+    const int nkb = K / BK;
+    if (splits < 1) splits = 1;
+    if (splits > nkb) splits = nkb;
+    const int per = (nkb + splits - 1) / splits;
+    splits = (nkb + per - 1) / per;
+    dim3 grid((M + BM - 1) / BM, (N + 63) / 64, splits);
+    cudaError_t err = exb::launch_pdl(exb_gemm_tcgen05_kernel<64>, grid, dim3(NUM_THREADS), gemm_smem<64>(),
+                                      (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err != cudaSuccess) { g_gemm_err = std::string("gemm_tn launch: ") + cudaGetErrorString(err); return -1; }
     return 0;
 }
 

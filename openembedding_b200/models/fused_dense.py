@@ -209,6 +209,8 @@ class FusedCTR:
         self.cache_off = torch.tensor(offs_c or [0], dtype=torch.int64, device=dev)
         # push+update runs on a second stream next to the dW GEMMs / dense optimizer (fork after dX1, join at step end)
         self.overlap = os.environ.get("EXB_OVERLAP", "0") == "1"
+        # weight-gradient GEMMs read the batch-major activations as MN-major operands: no A0^T / H^T / dZ^T copies
+        self.mn_major = os.environ.get("EXB_MN_MAJOR", "1") != "0"
         self._s2 = torch.cuda.Stream(device=dev)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         assert L <= 4, "the fused optimizer kernel takes at most 4 weight matrices"
@@ -260,7 +262,8 @@ class FusedCTR:
         self._mark("start")
         self.group.pull(ids, out=self.X32)
         self._mark("pull")
-        pa = _PrepArgs(self.X32.data_ptr(), self.XS, self.A0.data_ptr(), self.A0T.data_ptr(), ids.data_ptr(), self.nf,
+        tn = self.mn_major
+        pa = _PrepArgs(self.X32.data_ptr(), self.XS, self.A0.data_ptr(), 0 if tn else self.A0T.data_ptr(), ids.data_ptr(), self.nf,
                        dense.data_ptr(), self.nd, self.view("cache_emb").data_ptr(), self.view("cache_lin").data_ptr(),
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc, self.view("wd").data_ptr(),
                        self.view("bias").data_ptr(), self.S.data_ptr(), self.base.data_ptr(), B, self.K0p, self.Dp,
@@ -271,12 +274,12 @@ class FusedCTR:
         src = self.A0
         for l in range(L):
             G.gemm_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
-                      ones_col=self.Hp[l] - 1, outT=self.HT[l] if l < L - 1 else None, stream=st)
+                      ones_col=self.Hp[l] - 1, outT=self.HT[l] if (l < L - 1 and not tn) else None, stream=st)
             src = self.H[l]
         self._mark("fwd_gemm")
         ha = _HeadArgs(self.H[-1].data_ptr(), self.Hp[-1], self.Hp[-1] - 1, self.view("wout").data_ptr(),
                        self.base.data_ptr(), labels.data_ptr(), self.dlogit.data_ptr(), self.loss.data_ptr(),
-                       self.dZ[-1].data_ptr(), self.dZT[-1].data_ptr(), self.gview("wout").data_ptr(),
+                       self.dZ[-1].data_ptr(), 0 if tn else self.dZT[-1].data_ptr(), self.gview("wout").data_ptr(),
                        self.gview("wd").data_ptr(), self.gview("bias").data_ptr(), dense.data_ptr(), self.nd,
                        self.G32.data_ptr(), self.XS, self.lin0, self.ns, ids.data_ptr(), self.nf,
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
@@ -285,7 +288,7 @@ class FusedCTR:
         self._mark("head")
         for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
             G.gemm_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
-                      ones_col=self.Hp[l - 1] - 1, outT=self.dZT[l - 1], mask=self.H[l - 1], stream=st)
+                      ones_col=self.Hp[l - 1] - 1, outT=None if tn else self.dZT[l - 1], mask=self.H[l - 1], stream=st)
         G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
                   S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
         self._mark("dx_gemm")
@@ -300,6 +303,10 @@ class FusedCTR:
         for l in range(L):                 # dW_l = dZ_l^T @ H_{l-1}
             prevT = self.A0T if l == 0 else self.HT[l - 1]
             gW = self.gview("W%d" % l).view(self.Hp[l], dims[l])
+            if tn:
+                G.gemm_tn(self.dZ[l], self.A0 if l == 0 else self.H[l - 1], self.Hp[l], dims[l], B, gW,
+                          splits=self.dw_splits, stream=st)
+                continue
             G.gemm_nt(self.dZT[l], prevT, self.Hp[l], dims[l], B, gW, mode=G.EPI_DW, splits=self.dw_splits, stream=st)
         if self.nc:
             _ck(lib.exb_cachegrad(self.G32.data_ptr(), self.XS, self.ns * self.Dp, self.Dp, ids.data_ptr(), self.nf,

@@ -24,6 +24,9 @@ def _lib():
                                          c_int, c_uint64, c_longlong, c_uint64, c_longlong, c_uint64, c_longlong,
                                          c_uint64, c_uint64, c_uint64, c_longlong, c_int, c_int, c_int, c_uint64,
                                          c_uint64]
+        lib.exb_gemm_bf16_tn.restype = c_int
+        lib.exb_gemm_bf16_tn.argtypes = [c_uint64, c_longlong, c_uint64, c_longlong, c_int, c_int, c_int, c_uint64,
+                                         c_longlong, c_int, c_uint64]
         lib.exb_gemm_last_error.restype = ctypes.c_char_p
         _proto_done = True
     return lib
@@ -46,4 +49,20 @@ def gemm_nt(A, B, M, N, K, out, mode=EPI_FWD, relu=False, ones_col=-1, outT=None
                               emb.stride(0) if emb is not None else 0, fm_cols, D, splits, st, _p(dbg))
     if rc != 0:
         raise RuntimeError("exb_gemm_bf16_nt: " + lib.exb_gemm_last_error().decode())
+    return out
+
+
+def gemm_tn(A, B, M, N, K, out, splits=1, stream=None):
+    """out[M, N] (fp32) += A[K, M].T @ B[K, N] with A, B row-major bf16 (K rows): the weight-gradient
+    product straight from batch-major activations -- both operands are fed to the tensor core as
+    MN-major tiles, so no transposed copies have to be materialised. ``out`` must be zeroed (or
+    hold the value to accumulate onto); split-K partial sums arrive by TMA reduce-add."""
+    lib = _lib()
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    st = stream if stream is not None else torch.cuda.current_stream(A.device).cuda_stream
+    rc = lib.exb_gemm_bf16_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, out.data_ptr(),
+                              out.stride(0), splits, st)
+    if rc != 0:
+        raise RuntimeError("exb_gemm_bf16_tn: " + lib.exb_gemm_last_error().decode())
     return out

@@ -74,3 +74,17 @@ def test_dx_fm():
     ref[:, :F * D] += fm.reshape(Bsz, -1)
     assert torch.allclose(out[:, :N], ref, atol=5e-2, rtol=2e-2), (out[:, :N] - ref).abs().max()
     assert float(out[:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 64, 64, 1), (64, 64, 128, 1), (448, 1728, 4096, 8), (448, 448, 4096, 8),
+                                          (100, 72, 256, 2)])
+def test_dw_mn_major(M, N, K, splits):
+    """out = A[K,M]^T @ B[K,N] from batch-major operands (MN-major UMMA tiles, no transposed copies)"""
+    from openembedding_b200.ops.gemm import gemm_tn
+    ldm, ldn = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A, B = _mk(K, M, ld=ldm, scale=0.1, seed=11), _mk(K, N, ld=ldn, scale=0.1, seed=12)
+    out = torch.zeros(M, ldn, device="cuda", dtype=torch.float32)
+    gemm_tn(A[:, :M], B[:, :N], M, N, K, out[:, :N] if ldn == N else out, splits=splits)
+    torch.cuda.synchronize()
+    ref = A[:, :M].float().t() @ B[:, :N].float()
+    assert torch.allclose(out[:, :N], ref, atol=5e-2, rtol=2e-2), (out[:, :N] - ref).abs().max()

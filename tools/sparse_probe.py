@@ -21,6 +21,8 @@ ap.add_argument("--vocab", default="kaggle")
 ap.add_argument("--iters", type=int, default=6)
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--optimizer", default="adagrad")
+ap.add_argument("--ids", default="loguniform", choices=["loguniform", "sequential"],
+                help="sequential: consecutive rows per feature (DRAM-friendly) -- separates DRAM random-access cost from latency")
 a = ap.parse_args()
 oe.flags.device = "cuda"
 ctx = get_context()
@@ -33,7 +35,11 @@ gen = torch.Generator().manual_seed(0)
 v = torch.tensor(vocab, dtype=torch.float64)
 for it in range(a.iters):
     u = torch.rand((a.batch, 26), generator=gen, dtype=torch.float64)
-    ids = (torch.floor(torch.exp(u * torch.log(v))) - 1).clamp_(min=0).to(torch.int64).contiguous().to(dev)
+    ids = (torch.floor(torch.exp(u * torch.log(v))) - 1).clamp_(min=0).to(torch.int64)
+    if a.ids == "sequential":
+        base = torch.randint(0, 1 << 20, (26,), generator=gen)
+        ids = ((base[None, :] + torch.arange(a.batch)[:, None]) % torch.tensor(vocab)[None, :]).to(torch.int64)
+    ids = ids.contiguous().to(dev)
     m.G32.normal_()
     torch.cuda.synchronize()
     e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
