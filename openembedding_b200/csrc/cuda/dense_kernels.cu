@@ -147,6 +147,88 @@ __global__ void __launch_bounds__(256) exb_prep_b_kernel(PrepArgs a) {
     }
 }
 
+// prep, row-wise (Dp divides 128): ONE pass over X32 per batch row by one warp.
+//   lane l handles the float4 at columns 4l + 128 i, so its embedding sub-range d = (4l) % Dp is the
+//   same in every iteration: FM field sums and squares accumulate in registers, lanes that share
+//   d are combined with xor-shuffles at the end. The same pass writes the bf16 MLP input row
+//   (8 bytes per lane, 256 contiguous bytes per warp instruction), gathers the cached tables'
+//   rows (and copies them into X32 for the FM gradient), appends dense features / padding /
+//   the ones column, and reduces the linear terms into the per-sample base logit.
+//   Replaces prep A (column per thread, needed only while A0^T was materialised) + prep B
+//   (second pass over X32): 25 + 16 us -> see profiles/dense_path.md.
+__global__ void __launch_bounds__(256) exb_prep_row_kernel(PrepArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss) *a.loss = 0.f;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    const int emb_cols = a.nf * a.Dp, srv_cols = a.ns * a.Dp;
+    float* xr = a.X32 + (size_t)b * a.xs;
+    __nv_bfloat16* ar = a.A0 + (size_t)b * a.K0p;
+    const long long* idr = a.ids + (size_t)b * a.ncols;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float q = 0.f;
+    constexpr int U = 7;
+    for (int c0 = lane * 4; c0 < a.K0p; c0 += 128 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {           // batch of independent loads
+            const int c = c0 + 128 * u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < srv_cols) {
+                v[u] = *reinterpret_cast<const float4*>(xr + c);
+            } else if (c < emb_cols) {
+                const int cj = (c - srv_cols) / a.Dp, d = c % a.Dp;
+                const long long id = idr[a.cache_col[cj]];
+                v[u] = *reinterpret_cast<const float4*>(a.cache_emb + (size_t)(a.cache_off[cj] + id) * a.Dp + d);
+            } else if (c < a.K0p) {
+                float t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = c + e - emb_cols;
+                    t[e] = (k < a.nd) ? a.dense[(size_t)b * a.nd + k] : ((c + e == a.K0p - 1) ? 1.f : 0.f);
+                }
+                v[u] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 128 * u;
+            if (c >= a.K0p) continue;
+            if (c < emb_cols) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+                if (c >= srv_cols) *reinterpret_cast<float4*>(xr + c) = v[u];
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(ar + c) = pk;
+        }
+    }
+    // lanes l, l + Dp/4, l + 2 Dp/4, ... hold partial sums of the same d
+    for (int off = a.Dp >> 2; off < 32; off <<= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+    }
+    float fm = 0.f;
+    if (lane < (a.Dp >> 2)) {
+        *reinterpret_cast<float4*>(a.S + (size_t)b * a.Dp + lane * 4) = s;
+        fm = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+    }
+    // linear terms: server rows (pulled into X32), cached rows, dense features
+    float lin = 0.f;
+    for (int j = lane; j < a.ns; j += 32) lin += xr[a.lin0 + j];
+    for (int j = lane; j < a.nc; j += 32) lin += a.cache_lin[a.cache_off[j] + idr[a.cache_col[j]]];
+    for (int k = lane; k < a.nd; k += 32) lin += a.dense[(size_t)b * a.nd + k] * a.wd[k];
+    float tot = lin + (a.use_fm ? 0.5f * (fm - q) : 0.f);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if (lane == 0) a.base[b] = tot + a.bias[0];
+}
+
 struct HeadArgs {
     const __nv_bfloat16* H; int Hp, ones_col;     // last hidden activation [B, Hp]
     const float* wout;                            // [Hp] (ones_col entry = output bias)
@@ -254,57 +336,182 @@ __global__ void __launch_bounds__(256) exb_head_b_kernel(HeadArgs a) {
     atomicAdd(&a.g_wout[n], gw);
 }
 
+// head, row-wise (Hp <= 512): one warp per batch row, 4 rows per warp, 32 rows per CTA.
+//   pass 1: z = base + H[b,:] . wout (H row kept in registers), loss, dlogit
+//   pass 2: dZ[b,:] = dlogit * wout * relu'(H) straight from those registers; dlogit * H
+//           accumulates per lane into the output-weight gradient, reduced over the CTA's 32
+//           rows in shared memory -> one global atomic per (CTA, column)
+//   server linear-term gradients go to G32; the cached tables' linear gradients are produced
+//   by the cachegrad kernel (which already groups duplicate ids).
+// Replaces head A + head B (the second existed for the transposed dZ copy).
+#define EXB_HEAD_MAXP 8
+__global__ void __launch_bounds__(256) exb_head_row_kernel(HeadArgs a) {
+    exb::pdl_trigger();
+    exb::pdl_wait();
+    __shared__ float s_gw[512];
+    __shared__ float s_dl[32];
+    __shared__ float s_loss[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_gw[i] = 0.f;
+    __syncthreads();
+    const int np = a.Hp >> 1;                       // bf16x2 pairs per row
+    float2 wv[EXB_HEAD_MAXP], gw[EXB_HEAD_MAXP];
+#pragma unroll
+    for (int p = 0; p < EXB_HEAD_MAXP; ++p) {
+        const int n = lane + 32 * p;
+        wv[p] = (n < np) ? reinterpret_cast<const float2*>(a.wout)[n] : make_float2(0.f, 0.f);
+        gw[p] = make_float2(0.f, 0.f);
+    }
+    float lsum = 0.f;
+    // the warp's 4 rows are processed together: all H loads first, then 4 interleaved reductions
+    float2 hv[4][EXB_HEAD_MAXP];
+    float z[4], dlv[4];
+    const int brow = blockIdx.x * 32 + warp * 4;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int b = brow + rr;
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(a.H + (size_t)min(b, a.B - 1) * a.Hp);
+#pragma unroll
+        for (int p = 0; p < EXB_HEAD_MAXP; ++p) {
+            const int n = lane + 32 * p;
+            hv[rr][p] = (n < np && b < a.B) ? __bfloat1622float2(h2[n]) : make_float2(0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        z[rr] = 0.f;
+#pragma unroll
+        for (int p = 0; p < EXB_HEAD_MAXP; ++p) z[rr] += hv[rr][p].x * wv[p].x + hv[rr][p].y * wv[p].y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) z[rr] += __shfl_xor_sync(0xffffffffu, z[rr], o);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int b = brow + rr;
+        dlv[rr] = 0.f;
+        if (b < a.B) {                              // warp uniform
+            const float zz = z[rr] + a.base[b];
+            const float y = a.labels[b];
+            lsum += (fmaxf(zz, 0.f) - zz * y + log1pf(expf(-fabsf(zz)))) * a.grad_scale;   // stable BCE with logits
+            dlv[rr] = (1.f / (1.f + expf(-zz)) - y) * a.grad_scale;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int b = brow + rr;
+        const float dl = dlv[rr];
+        if (b < a.B) {
+            if (lane == 0) a.dlogit[b] = dl;
+            for (int j = lane; j < a.ns; j += 32) a.G32[(size_t)b * a.xs + a.lin0 + j] = dl;
+            __nv_bfloat162* dz2 = reinterpret_cast<__nv_bfloat162*>(a.dZ + (size_t)b * a.Hp);
+#pragma unroll
+            for (int p = 0; p < EXB_HEAD_MAXP; ++p) {
+                const int n = lane + 32 * p;
+                if (n >= np) continue;
+                gw[p].x += dl * hv[rr][p].x; gw[p].y += dl * hv[rr][p].y;
+                const float dx = (hv[rr][p].x > 0.f && 2 * n != a.ones_col) ? dl * wv[p].x : 0.f;
+                const float dy = (hv[rr][p].y > 0.f && 2 * n + 1 != a.ones_col) ? dl * wv[p].y : 0.f;
+                dz2[n] = __floats2bfloat162_rn(dx, dy);
+            }
+        }
+        if (lane == 0) s_dl[warp * 4 + rr] = dl;
+    }
+#pragma unroll
+    for (int p = 0; p < EXB_HEAD_MAXP; ++p) {
+        const int n = lane + 32 * p;
+        if (n < np) { atomicAdd(&s_gw[2 * n], gw[p].x); atomicAdd(&s_gw[2 * n + 1], gw[p].y); }
+    }
+    if (lane == 0) s_loss[warp] = lsum;
+    __syncthreads();
+    for (int n = threadIdx.x; n < a.Hp; n += blockDim.x) atomicAdd(&a.g_wout[n], s_gw[n]);
+    if (threadIdx.x == 0) {
+        float t = 0.f, gb = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_loss[i];
+        for (int i = 0; i < 32; ++i) gb += s_dl[i];
+        atomicAdd(a.loss, t);
+        atomicAdd(a.g_bias, gb);
+    }
+    if ((int)threadIdx.x < a.nd) {     // dense-linear weight gradient, reduced over the CTA's 32 rows
+        float g = 0.f;
+        for (int r = 0; r < 32; ++r) {
+            const int bb = blockIdx.x * 32 + r;
+            if (bb < a.B) g += s_dl[r] * a.dense[(size_t)bb * a.nd + threadIdx.x];
+        }
+        atomicAdd(&a.g_wd[threadIdx.x], g);
+    }
+}
+
 // Scatter-add the gradient rows of the cached (replicated) embedding tables.
-// One warp per (32 batch rows, cached feature): the 32 gradient rows go through a per-warp
-// shared-memory tile, rows with the SAME id are summed there (__match_any_sync groups), and one
-// red.global.add.v4 per (distinct id, 4 columns) leaves the warp. Cached tables are the
-// small-vocabulary ones (3..4096 rows), so a batch hits each row up to thousands of times; the
-// first version issued one global atomic per (sample, 4 columns) and serialised on those rows.
+// CTA = (cached feature, 256 batch rows), warp = 32 rows. The 32 gradient rows go through a
+// per-warp shared-memory tile; rows with the SAME id are grouped with __match_any_sync, the first
+// row of a group (its leader) owns the sum. The (row, 4-column chunk) pairs are then spread over
+// the lanes: a pair whose row is a leader adds up the group's tile rows and issues one
+// red.global.add.v4 -- distinct ids proceed in parallel (a large-vocabulary tile is 16 fully
+// parallel steps), duplicates cost one shared-memory read each instead of a global atomic.
+// Cached tables are the small-vocabulary ones (3..4096 rows): the first version issued one global
+// atomic per (sample, chunk) and serialised on the hot rows. Shared-memory float atomics were
+// tried for the tiniest tables and were 1.5x slower (profiles/dense_path.md).
+// The kernel also produces the cached tables' linear-term gradients (dlogit summed per id).
 #define EXB_CG_MAXDP 128
 __global__ void __launch_bounds__(256) exb_cachegrad_kernel(const float* G32, long long xs, int col0, int Dp,
                                                             const long long* ids, int ncols, const int* cache_col,
                                                             const long long* cache_off, int nc, float* g_cache_emb,
-                                                            int B) {
+                                                            int B, const float* dlogit, float* g_cache_lin) {
     exb::pdl_trigger();
     extern __shared__ __align__(16) float cg_smem[];
+    __shared__ unsigned s_mem[8][32];       // group mask of a leader row, 0 otherwise
+    __shared__ long long s_id[8][32];
+    __shared__ float s_dl[8][32];
     exb::pdl_wait();
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    float* tile = cg_smem + (size_t)wic * 32 * Dp;
     const int chunks = Dp >> 2;
-    const int ntask = ((B + 31) / 32) * nc;
-    for (int task = warp; task < ntask; task += nwarps) {
-        const int j = task % nc, b0 = (task / nc) * 32;
-        const int b = b0 + lane;
-        const long long id = (b < B) ? ids[(size_t)b * ncols + cache_col[j]] : -1ll - lane;
-        const float* src = G32 + (size_t)b0 * xs + col0 + j * Dp;
-        for (int idx = lane; idx < 32 * chunks; idx += 32) {       // coalesced: consecutive lanes, consecutive float4
+    const int j = blockIdx.x % nc, blk = blockIdx.x / nc;
+    float* tile = cg_smem + (size_t)wic * 32 * Dp;
+    const int b0 = blk * 256 + wic * 32;
+    if (b0 >= B) return;
+    const int b = b0 + lane;
+    const long long id = (b < B) ? ids[(size_t)b * ncols + cache_col[j]] : -1ll - lane;
+    const float* src = G32 + (size_t)b0 * xs + col0 + j * Dp;
+    constexpr int LU = 8;                                       // batches of independent loads
+    for (int i0 = 0; i0 < chunks; i0 += LU) {                   // idx = lane + 32 i: coalesced float4s
+        float4 v[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int idx = lane + 32 * (i0 + u);
             const int r = idx / chunks, c = idx - r * chunks;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + r < B) v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * xs) + c);
-            reinterpret_cast<float4*>(tile)[idx] = v;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i0 + u < chunks && b0 + r < B) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * xs) + c);
         }
-        const unsigned grp = __match_any_sync(0xffffffffu, id);
-        unsigned leaders = __ballot_sync(0xffffffffu, b < B && lane == __ffs(grp) - 1);
-        __syncwarp();
-        const long long base = cache_off[j];
-        while (leaders) {                                           // warp-uniform
-            const int L = __ffs(leaders) - 1;
-            leaders &= leaders - 1;
-            const unsigned members = __shfl_sync(0xffffffffu, grp, L);
-            const long long lid = __shfl_sync(0xffffffffu, id, L);
-            float* dst = g_cache_emb + (size_t)(base + lid) * Dp;
-            for (int c = lane; c < chunks; c += 32) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (unsigned m = members; m; m &= m - 1) {
-                    const float4 v = reinterpret_cast<const float4*>(tile)[(__ffs(m) - 1) * chunks + c];
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 4), "f"(acc.x), "f"(acc.y),
-                             "f"(acc.z), "f"(acc.w) : "memory");
-            }
+#pragma unroll
+        for (int u = 0; u < LU; ++u)
+            if (i0 + u < chunks) reinterpret_cast<float4*>(tile)[lane + 32 * (i0 + u)] = v[u];
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, id);
+    s_mem[wic][lane] = (b < B && lane == __ffs(grp) - 1) ? grp : 0u;
+    s_id[wic][lane] = id;
+    s_dl[wic][lane] = (g_cache_lin != nullptr && b < B) ? dlogit[b] : 0.f;
+    __syncwarp();
+    const long long base = cache_off[j];
+    for (int i = 0; i < chunks; ++i) {
+        const int idx = lane + 32 * i;
+        const int r = idx / chunks, c = idx - r * chunks;
+        const unsigned members = s_mem[wic][r];
+        if (!members) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dl = 0.f;
+        for (unsigned m = members; m; m &= m - 1) {
+            const int q = __ffs(m) - 1;
+            const float4 v = reinterpret_cast<const float4*>(tile)[q * chunks + c];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            if (c == 0) dl += s_dl[wic][q];
         }
-        __syncwarp();
+        const long long row = base + s_id[wic][r];
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g_cache_emb + (size_t)row * Dp + c * 4), "f"(acc.x),
+                     "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+        if (c == 0 && g_cache_lin != nullptr) atomicAdd(&g_cache_lin[row], dl);
     }
 }
 
@@ -326,7 +533,9 @@ struct DenseOptArgs {
 
 __device__ __forceinline__ float adagrad_one(float& w, float& a, float g, float lr, float eps) {
     a += g * g;
-    w -= lr * g / (sqrtf(a) + eps);
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));      // 1 ulp; the IEEE sequences made this kernel issue bound
+    w -= __fdividef(lr * g, r + eps);
     return w;
 }
 
@@ -340,21 +549,28 @@ __device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*ti
         const int G = (int)gridDim.x;
         for (int t = ((int)blockIdx.x - tile_base % G + G) % G; t < nt; t += G) {
             const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
-            for (int i = ty; i < 32; i += 8) {
-                const int r = r0 + i, c = c0 + tx;
-                float w = 0.f;
+            float g4[4], a4[4], w4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {          // 12 independent loads in flight per thread
+                const int r = r0 + ty + 8 * u, c = c0 + tx;
+                g4[u] = a4[u] = w4[u] = 0.f;
                 if (r < M.R && c < M.C) {
                     const long long k = M.off + (long long)r * M.C + c;
-                    const float g = __ldcg(o.grad + k);
-                    float a = o.accum[k];
-                    w = o.theta[k];
-                    adagrad_one(w, a, g, o.lr, o.eps);
-                    o.accum[k] = a;
-                    o.theta[k] = w;
-                    if (o.zero_grad) o.grad[k] = 0.f;
-                    M.Wb[(size_t)r * M.C + c] = __float2bfloat16_rn(w);
+                    g4[u] = __ldcg(o.grad + k); a4[u] = o.accum[k]; w4[u] = o.theta[k];
                 }
-                tile[i][tx] = w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = ty + 8 * u, r = r0 + i, c = c0 + tx;
+                if (r < M.R && c < M.C) {
+                    const long long k = M.off + (long long)r * M.C + c;
+                    adagrad_one(w4[u], a4[u], g4[u], o.lr, o.eps);
+                    o.accum[k] = a4[u];
+                    o.theta[k] = w4[u];
+                    if (o.zero_grad) o.grad[k] = 0.f;
+                    M.Wb[(size_t)r * M.C + c] = __float2bfloat16_rn(w4[u]);
+                }
+                tile[i][tx] = w4[u];
             }
             __syncthreads();
             for (int i = ty; i < 32; i += 8) {
@@ -536,34 +752,45 @@ int exb_prep(const void* args, int B, int Dp, uint64_t stream) {
     PrepArgs a = *reinterpret_cast<const PrepArgs*>(args);
     (void)Dp;
     dim3 ga((B + 31) / 32, (a.K0p + 255) / 256);
-    cudaError_t e = exb::launch_pdl(exb_prep_a_kernel, ga, dim3(256), 0, (cudaStream_t)stream, a);
-    if (e == cudaSuccess) e = exb::launch_pdl(exb_prep_b_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
+    cudaError_t e;
+    if (a.A0T == nullptr && a.Dp >= 4 && 128 % a.Dp == 0 && a.K0p % 4 == 0) {   // one row-wise pass
+        e = exb::launch_pdl(exb_prep_row_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
+    } else {
+        e = exb::launch_pdl(exb_prep_a_kernel, ga, dim3(256), 0, (cudaStream_t)stream, a);
+        if (e == cudaSuccess) e = exb::launch_pdl(exb_prep_b_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
+    }
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
 int exb_prep_args_size() { return (int)sizeof(PrepArgs); }
 int exb_head(const void* args, int B, uint64_t stream) {
     HeadArgs a = *reinterpret_cast<const HeadArgs*>(args);
-    cudaError_t e = exb::launch_pdl(exb_head_a_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
-    dim3 gb((B + 31) / 32, (a.Hp + 255) / 256);
-    if (e == cudaSuccess) e = exb::launch_pdl(exb_head_b_kernel, gb, dim3(256), 0, (cudaStream_t)stream, a);
+    cudaError_t e;
+    if (a.dZT == nullptr && a.Hp <= 64 * EXB_HEAD_MAXP && a.Hp % 2 == 0 && a.g_cache_lin == nullptr) {
+        e = exb::launch_pdl(exb_head_row_kernel, dim3((B + 31) / 32), dim3(256), 0, (cudaStream_t)stream, a);
+    } else {
+        e = exb::launch_pdl(exb_head_a_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a);
+        dim3 gb((B + 31) / 32, (a.Hp + 255) / 256);
+        if (e == cudaSuccess) e = exb::launch_pdl(exb_head_b_kernel, gb, dim3(256), 0, (cudaStream_t)stream, a);
+    }
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }
 int exb_head_args_size() { return (int)sizeof(HeadArgs); }
 int exb_cachegrad(uint64_t G32, long long xs, int col0, int Dp, uint64_t ids, int ncols, uint64_t cache_col,
-                  uint64_t cache_off, int nc, uint64_t g_cache_emb, int B, uint64_t stream) {
+                  uint64_t cache_off, int nc, uint64_t g_cache_emb, int B, uint64_t dlogit, uint64_t g_cache_lin,
+                  uint64_t cache_vocab, uint64_t stream) {
     if (nc == 0) return 0;
     if (Dp % 4 || Dp > EXB_CG_MAXDP) { g_dense_err = "cachegrad: Dp must be a multiple of 4 and <= 128"; return -1; }
-    const int ntask = ((B + 31) / 32) * nc;
-    int grid = (ntask + 7) / 8;
-    if (grid > 148 * 4) grid = 148 * 4;
+    const int grid = nc * ((B + 255) / 256);     // CTA = (cached feature, 256 batch rows)
     const size_t smem = (size_t)8 * 32 * Dp * sizeof(float);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(exb_cachegrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * EXB_CG_MAXDP * 4); attr = true; }
     cudaError_t e = exb::launch_pdl(exb_cachegrad_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const float*)G32,
                                     xs, col0, Dp, (const long long*)ids, ncols, (const int*)cache_col,
-                                    (const long long*)cache_off, nc, (float*)g_cache_emb, B);
+                                    (const long long*)cache_off, nc, (float*)g_cache_emb, B, (const float*)dlogit,
+                                    (float*)g_cache_lin);
+    (void)cache_vocab;
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;
 }

@@ -32,10 +32,14 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-// BN = 64: 96 KB of stages, two CTAs per SM (small-N GEMMs); BN = 256: 192 KB, one CTA per SM,
-// 4x fewer re-reads of the A operand (the wide dX1 / dW1 GEMMs are L2-bandwidth bound at BN = 64)
+// Tile width. The GEMMs of a step are bound by operand traffic out of L2, not by the tensor cores
+// (measured: time ~ bytes each SM pulls / ~42 B/clk): a 128x64 tile re-reads (1/128 + 1/64) operand
+// bytes per output element, a 128x128 tile (1/128 + 1/128), a third less.
+//   BN = 64 : 4 stages x 24 KB = 96 KB, two CTAs per SM -- the small GEMMs (K = 448, 224 tiles)
+//   BN = 128: 3 stages x 32 KB = 96 KB, two CTAs per SM -- the wide ones (fwd1, dX1, dW1)
+template <int BN> constexpr int stages_for() { return BN == 64 ? 4 : 3; }
 constexpr int NUM_THREADS = 192;
 
 enum EpiMode : int { EPI_FWD = 0, EPI_DX = 1, EPI_DW = 2, EPI_DX_FM = 3 };
@@ -47,6 +51,7 @@ struct GemmEpi {
     __nv_bfloat16* outT; long long ldoT;
     const __nv_bfloat16* mask; long long ldmask;
     const float* dlogit; const float* S; const float* emb; long long ldemb;
+    int swap, _pad2;
     unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) [start, setup, first-full, mainloop, epilogue]
 };
 
@@ -117,12 +122,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, (BN <= 64 ? 2 : 1))
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmT,
                         GemmEpi E, int num_k_blocks, int k_blocks_per_split) {
-    static_assert(BN == 64, "the TMA-store epilogue stages one 64-column tile per warp");
+    static_assert(BN == 64 || BN == 128, "tile width");
+    constexpr int STAGES = stages_for<BN>();
     constexpr int B_BYTES = BN * BK * 2;
+    constexpr int WSTAGE = BN * 128, TSTAGE = BN * 64;     // per-warp epilogue staging: out tiles | outT tile
+    static_assert(4 * (WSTAGE + TSTAGE) <= STAGES * (A_BYTES + B_BYTES), "epilogue staging aliases the stage memory");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases; do not rely on the toolchain for it
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -135,7 +143,8 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
     exb::pdl_trigger();   // the next kernel of the step may be scheduled once all CTAs are resident
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+    // E.swap: N tiles vary fastest over the launch order (neighbouring CTAs share the A tile, not the B tile)
+    const int m_blk = E.swap ? blockIdx.y : blockIdx.x, n_blk = E.swap ? blockIdx.x : blockIdx.y;
     const bool dbg = E.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define GSTAMP(i) do { if (dbg) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); E.dbg[i] = _t; } } while (0)
     if (threadIdx.x == 0) GSTAMP(0);
@@ -171,7 +180,9 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (E.mn_major) {   // boxes of 64 MN elements x 64 k rows; the A tile is two MN blocks
                     tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], m_blk * BM, (kb0 + i) * BK);
                     tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], m_blk * BM + 64, (kb0 + i) * BK);
-                    tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], n_blk * BN, (kb0 + i) * BK);
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h)
+                        tma_load_2d(sB + s * B_BYTES + h * 8192, &tmB, &full[s], n_blk * BN + 64 * h, (kb0 + i) * BK);
                     continue;
                 }
                 tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + i) * BK, m_blk * BM);
@@ -194,7 +205,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     const uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem_base, umma_desc_mn(a0 + k * 2048, A_BYTES / 2), umma_desc_mn(b0 + k * 2048, B_BYTES),
+                        umma_bf16(tmem_base, umma_desc_mn(a0 + k * 2048, 8192), umma_desc_mn(b0 + k * 2048, 8192),
                                   idesc_mn, (i | k) ? 1u : 0u);
                 } else {
 #pragma unroll
@@ -215,8 +226,8 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int q = warp & 3;
         const int row0 = m_blk * BM + q * 32, row = row0 + lane;
         const bool rv = row < E.M;
-        uint8_t* wstage = smem + (warp - 2) * 12288;          // per warp: 8 KB out tile(s) + 4 KB outT tile
-        uint8_t* tstage = wstage + 8192;
+        uint8_t* wstage = smem + (warp - 2) * (WSTAGE + TSTAGE);   // per warp: out tile(s) | outT tile
+        uint8_t* tstage = wstage + WSTAGE;
         const bool f32out = (E.mode == EPI_DW || E.mode == EPI_DX_FM);
         bool ok = true, waited = false;
 #pragma unroll 1
@@ -291,7 +302,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                                      ::"l"(&tmO), "r"(smem_u32(tile)), "r"(n0), "r"(row0) : "memory");
                 }
             } else {
-                uint8_t* tile = wstage;                           // [32 rows][64 bf16], both chunks
+                uint8_t* tile = wstage + (c0 >> 6) * 4096;        // [32 rows][64 bf16] per 64 columns
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     uint32_t pk[4];
@@ -300,7 +311,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * u]), __uint_as_float(v[8 * t + 2 * u + 1]));
                         pk[u] = *reinterpret_cast<uint32_t*>(&h2);
                     }
-                    const int chunk = (c0 >> 3) + t;
+                    const int chunk = ((c0 & 63) >> 3) + t;
                     *reinterpret_cast<uint4*>(tile + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 if (E.outT) {                                     // [64 n][32 rows] bf16: lanes along the row axis
@@ -314,8 +325,10 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0 && E.fm_cols != -7) {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                             ::"l"(&tmO), "r"(smem_u32(wstage)), "r"(n_blk * BN), "r"(row0) : "memory");
+#pragma unroll
+                for (int h = 0; h < BN / 64; ++h)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmO), "r"(smem_u32(wstage + h * 4096)), "r"(n_blk * BN + 64 * h), "r"(row0) : "memory");
                 if (E.outT)
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                  ::"l"(&tmT), "r"(smem_u32(tstage)), "r"(row0), "r"(n_blk * BN) : "memory");
@@ -376,7 +389,35 @@ bool make_map_ex(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void
 }
 
 template <int BN>
-constexpr size_t gemm_smem() { return STAGES * (A_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+constexpr size_t gemm_smem() { return stages_for<BN>() * (A_BYTES + BN * BK * 2) + (2 * stages_for<BN>() + 1) * 8 + 16 + 1024; }
+
+// tile width: env EXB_GEMM_BN (64 | 128) overrides; default 128 for the operand-traffic bound shapes
+int pick_swap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EXB_GEMM_SWAP"); v = e ? atoi(e) : 0; }
+    return v;
+}
+int pick_bn(int M, int N, int K) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("EXB_GEMM_BN"); forced = e ? atoi(e) : 0; }
+    if (forced == 64 || forced == 128) return forced;
+    // measured (profiles/dense_path.md): 128-wide tiles cut operand traffic by a third but leave too few
+    // CTAs in flight per SM for this step's shapes (fwd1 15.0 -> 17.0 us, dX1 32.9 -> 35.6 us); default 64
+    (void)M; (void)N; (void)K;
+    return 64;
+}
+
+template <int BN>
+cudaError_t launch_gemm(dim3 grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                        const CUtensorMap& tmT, const GemmEpi& E, int nkb, int per) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
+        attr_set = true;
+    }
+    return exb::launch_pdl(exb_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), gemm_smem<BN>(), stream, tmA, tmB, tmO, tmT,
+                           E, nkb, per);
+}
 
 }  // namespace
 
@@ -393,7 +434,7 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     if (K % BK != 0 || lda % 8 != 0 || ldb % 8 != 0) { g_gemm_err = "gemm: K %% 64 / ld %% 8 violated"; return -1; }
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, (const void*)A, M, K, lda, BM)) return -1;
-    const int BN = 64;   // a BN=256 variant measured slower: the per-CTA epilogue dominated (profiles/gemm.md)
+    const int BN = pick_bn(M, N, K);
     if (!make_map(&tmB, (const void*)B, N, K, ldb, BN)) return -1;
     CUtensorMap tmO, tmT;
     const bool f32out = (mode == EPI_DW || mode == EPI_DX_FM);
@@ -403,26 +444,23 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
         if (!make_map_ex(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)out, M, (N + 63) / 64 * 64, ldo, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     }
     tmT = tmO;
-    if (outT && !make_map_ex(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)outT, (N + 63) / 64 * 64, M, ldoT, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    if (outT && !make_map_ex(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)outT, (N + 63) / 64 * 64, M, ldoT, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     GemmEpi E;
     E.mode = mode; E.relu = relu; E.ones_col = ones_col; E.fm_cols = fm_cols; E.M = M; E.N = N; E.D = D > 0 ? D : 1; E.mn_major = 0;
     E.out = (void*)out; E.ldo = ldo; E.outT = (__nv_bfloat16*)outT; E.ldoT = ldoT;
     E.mask = (const __nv_bfloat16*)mask; E.ldmask = ldmask;
     E.dlogit = (const float*)dlogit; E.S = (const float*)S; E.emb = (const float*)emb; E.ldemb = ldemb;
     E.dbg = (unsigned long long*)dbg;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
-        attr_set = true;
-    }
     const int nkb = K / BK;
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    cudaError_t err = exb::launch_pdl(exb_gemm_tcgen05_kernel<64>, grid, dim3(NUM_THREADS), gemm_smem<64>(),
-                                      (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
+    E.swap = pick_swap(); E._pad2 = 0;
+    if (E.swap) grid = dim3(grid.y, grid.x, grid.z);
+    cudaError_t err = BN == 128 ? launch_gemm<128>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per)
+                                : launch_gemm<64>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(err); return -1; }
     return 0;
@@ -444,19 +482,17 @@ int exb_gemm_bf16_tn(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     memset(&E, 0, sizeof(E));
     E.mode = EPI_DW; E.ones_col = -1; E.M = M; E.N = N; E.D = 1; E.mn_major = 1;
     E.out = (void*)out; E.ldo = ldo;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
-        attr_set = true;
-    }
+    const int BN = pick_bn(M, N, K);
     const int nkb = K / BK;
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
-    dim3 grid((M + BM - 1) / BM, (N + 63) / 64, splits);
-    cudaError_t err = exb::launch_pdl(exb_gemm_tcgen05_kernel<64>, grid, dim3(NUM_THREADS), gemm_smem<64>(),
-                                      (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+    E.swap = pick_swap(); E._pad2 = 0;
+    if (E.swap) grid = dim3(grid.y, grid.x, grid.z);
+    cudaError_t err = BN == 128 ? launch_gemm<128>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per)
+                                : launch_gemm<64>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm_tn launch: ") + cudaGetErrorString(err); return -1; }
     return 0;

@@ -76,7 +76,8 @@ def _lib():
         lib.exb_prep_args_size.restype = c_int
         lib.exb_head_args_size.restype = c_int
         lib.exb_cachegrad.restype = c_int
-        lib.exb_cachegrad.argtypes = [u64, c_longlong, c_int, c_int, u64, c_int, u64, u64, c_int, u64, c_int, u64]
+        lib.exb_cachegrad.argtypes = [u64, c_longlong, c_int, c_int, u64, c_int, u64, u64, c_int, u64, c_int, u64, u64, u64,
+                                      u64]
         lib.exb_adagrad_flat.restype = c_int
         lib.exb_adagrad_flat.argtypes = [u64, u64, u64, c_longlong, c_float, c_float, u64]
         lib.exb_refresh_bf16.restype = c_int
@@ -122,7 +123,7 @@ class FusedCTR:
             hidden = (400, 400, 400) if self.use_fm else (512, 256, 128, 32)
         self.hidden = list(hidden)
         self.Hp = [_r(h + 1, 64) for h in self.hidden]
-        self.lr, self.eps, self.dw_splits = lr, eps, dw_splits
+        self.lr, self.eps, self.dw_splits = lr, eps, int(os.environ.get("EXB_DW_SPLITS", dw_splits))
         self.cached = [f for f, v in enumerate(self.vocab) if 0 < v < cache_threshold]
         self.server = [f for f in range(self.nf) if f not in self.cached]
         self.ns, self.nc = len(self.server), len(self.cached)
@@ -207,6 +208,7 @@ class FusedCTR:
             o += self.vocab[f]
         self.cache_col = torch.tensor(self.cached or [0], dtype=torch.int32, device=dev)
         self.cache_off = torch.tensor(offs_c or [0], dtype=torch.int64, device=dev)
+        self.cache_vocab = torch.tensor([self.vocab[f] for f in self.cached] or [0], dtype=torch.int32, device=dev)
         # push+update runs on a second stream next to the dW GEMMs / dense optimizer (fork after dX1, join at step end)
         self.overlap = os.environ.get("EXB_OVERLAP", "0") == "1"
         # weight-gradient GEMMs read the batch-major activations as MN-major operands: no A0^T / H^T / dZ^T copies
@@ -277,13 +279,14 @@ class FusedCTR:
                       ones_col=self.Hp[l] - 1, outT=self.HT[l] if (l < L - 1 and not tn) else None, stream=st)
             src = self.H[l]
         self._mark("fwd_gemm")
+        row_head = tn and self.Hp[-1] <= 512       # merged row-wise head; cachegrad then owns the cached linear grads
         ha = _HeadArgs(self.H[-1].data_ptr(), self.Hp[-1], self.Hp[-1] - 1, self.view("wout").data_ptr(),
                        self.base.data_ptr(), labels.data_ptr(), self.dlogit.data_ptr(), self.loss.data_ptr(),
                        self.dZ[-1].data_ptr(), 0 if tn else self.dZT[-1].data_ptr(), self.gview("wout").data_ptr(),
                        self.gview("wd").data_ptr(), self.gview("bias").data_ptr(), dense.data_ptr(), self.nd,
                        self.G32.data_ptr(), self.XS, self.lin0, self.ns, ids.data_ptr(), self.nf,
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
-                       self.gview("cache_lin").data_ptr(), B, 1.0 / B)
+                       0 if row_head else self.gview("cache_lin").data_ptr(), B, 1.0 / B)
         _ck(lib.exb_head(ctypes.byref(ha), B, st), "head")
         self._mark("head")
         for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
@@ -311,7 +314,9 @@ class FusedCTR:
         if self.nc:
             _ck(lib.exb_cachegrad(self.G32.data_ptr(), self.XS, self.ns * self.Dp, self.Dp, ids.data_ptr(), self.nf,
                                   self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
-                                  self.gview("cache_emb").data_ptr(), B, st), "cachegrad")
+                                  self.gview("cache_emb").data_ptr(), B, self.dlogit.data_ptr(),
+                                  self.gview("cache_lin").data_ptr() if row_head else 0,
+                                  self.cache_vocab.data_ptr(), st), "cachegrad")
         self._mark("dw_gemm+cachegrad")
         if update:
             if not forked:
@@ -335,7 +340,9 @@ class FusedCTR:
     def kernels_per_step(self):
         """launches of our own kernels in one training step"""
         L = len(self.hidden)
-        n = 1 + 2 + L + 2 + L + L + (1 if self.nc else 0) + 1 + 1   # pull prep(2) fwd head(2) dX dW cache push optimizer
+        prep = 1 if (self.mn_major and 128 % self.Dp == 0) else 2
+        head = 1 if (self.mn_major and self.Hp[-1] <= 512) else 2
+        n = 1 + prep + L + head + L + L + (1 if self.nc else 0) + 1 + 1   # pull prep fwd head dX dW cache push optimizer
         return n     # world > 1: the fused all-reduce+Adagrad kernel replaces the Adagrad launch
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)

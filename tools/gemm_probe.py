@@ -11,6 +11,7 @@ cases = {
   "fwd1-nostore M4096 N448 K1728": dict(A=mk(B, 1728), Bm=mk(448, 1728), M=B, N=448, K=1728, mode=EPI_FWD, out=torch.zeros(B, 448, device=dev, dtype=torch.bfloat16), outT=torch.zeros(448, B, device=dev, dtype=torch.bfloat16), nostore=True),
   "dX1   M4096 N1728 K448": dict(A=mk(B, 448), Bm=mk(1728, 448), M=B, N=1728, K=448, mode=EPI_DX_FM, out=torch.zeros(B, 1756, device=dev), fm=True),
   "dX1nf M4096 N1728 K448": dict(A=mk(B, 448), Bm=mk(1728, 448), M=B, N=1728, K=448, mode=EPI_DX_FM, out=torch.zeros(B, 1756, device=dev), fm=False),
+  "fwd2  M4096 N448 K448": dict(A=mk(B, 448), Bm=mk(448, 448), M=B, N=448, K=448, mode=EPI_FWD, out=torch.zeros(B, 448, device=dev, dtype=torch.bfloat16)),
   "dW1   M448 N1728 K4096": dict(A=mk(448, B), Bm=mk(1728, B), M=448, N=1728, K=B, mode=EPI_DW, out=torch.zeros(448, 1728, device=dev), splits=8),
 }
 emb = torch.randn(B, 1756, device=dev); S = torch.randn(B, 64, device=dev); dl = torch.randn(B, device=dev)
