@@ -684,14 +684,14 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     size_t woff = 0;
     auto wtake = [&](size_t bytes) { size_t o = woff; woff = align_up(woff + bytes, 256); return o; };
     size_t o_send = wtake((size_t)W * PT * 4 * EXB_CTR_STRIDE), o_ucount = wtake((size_t)PT * 4 * EXB_CTR_STRIDE), o_ckeys = wtake(mo * 8), o_ccnt = wtake(mo * 4),
-           o_ulist = wtake(uo * 4), o_acc = wtake(ao * 4);
+           o_ulist = wtake(uo * 4), o_ukeys = wtake(uo * 8), o_acc = wtake(ao * 4);
     CKP(cudaMalloc(&p->work, woff));
     CKP(cudaMemset(p->work, 0, woff));
     fill_u64_kernel<<<e->sms * 4, 256>>>((unsigned long long*)(p->work + o_ckeys), mo, EXB_EMPTY_KEY);
     CKP(cudaGetLastError());
     d.send_cnt = (unsigned*)(p->work + o_send); d.ucount = (unsigned*)(p->work + o_ucount);
     d.cmap_keys = (unsigned long long*)(p->work + o_ckeys); d.cmap_cnt = (unsigned*)(p->work + o_ccnt);
-    d.ulist = (unsigned*)(p->work + o_ulist); d.acc = (float*)(p->work + o_acc);
+    d.ulist = (unsigned*)(p->work + o_ulist); d.ukeys = (unsigned long long*)(p->work + o_ukeys); d.acc = (float*)(p->work + o_acc);
     // ---- sync words
     for (int r = 0; r < W; ++r) d.flags[r] = (unsigned*)(e->sync_peer[r] + OFF_FLAGS);
     d.gbar = (unsigned*)(e->sync_local + OFF_GBAR);

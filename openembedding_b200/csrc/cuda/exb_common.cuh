@@ -62,6 +62,7 @@ struct PlanDev {
     unsigned* cmap_cnt;
     float* acc;
     unsigned* ulist;
+    unsigned long long* ukeys;                      // key of every unique-list entry (parallel to ulist)
     unsigned* ucount;                               // [PT]
     unsigned* flags[EXB_MAX_PEERS];                 // peer mapped [W]
     unsigned* gbar;                                 // [0] arrive count, [1] generation

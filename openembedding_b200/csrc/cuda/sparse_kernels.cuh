@@ -280,7 +280,11 @@ __device__ __forceinline__ unsigned cmap_insert_warp(const PlanDev& P, const Sme
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(&P.ucount[pt * EXB_CTR_STRIDE], (unsigned)__popc(wmask));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (won) P.ulist[S.ulist_off[pt] + base + (unsigned)__popc(wmask & ((1u << lane) - 1u))] = h;
+        if (won) {
+            const unsigned long long up = S.ulist_off[pt] + base + (unsigned)__popc(wmask & ((1u << lane) - 1u));
+            P.ulist[up] = h;
+            P.ukeys[up] = key;     // the apply phase reads key and slot side by side (one dependent load less)
+        }
     }
     return active ? h : 0xFFFFFFFFu;
 }
@@ -369,26 +373,48 @@ __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, in
     __syncthreads();
 }
 
-// unique rows per warp task of the apply phase: what fits the warp's row buffer in ONE pass
-// (dim 64 + Adagrad: 13). Finer tasks than 32 rows balance the phase: with 32-row tasks the
-// slowest warp walked 6 buffer passes while the average warp needed 2.6.
-__device__ __forceinline__ int apply_chunk(const TableDev& T, int use_bulk) {
-    const unsigned need = (2u * (unsigned)T.wstride + (unsigned)T.sstride) * 4u;
-    if (use_bulk && T.vec4 && need <= EXB_APPLY_WARP_BUF) return min(32, (int)(EXB_APPLY_WARP_BUF / need));
-    return 32;
+// ---- work split of the apply phase ----------------------------------------------------
+// A warp task is `chunk` unique rows of one table, gathered in ONE pass through the warp's row
+// buffer (weights + state + accumulated gradient). The chunk is chosen per step from the actual
+// unique counts: the phase is split into the smallest number of rounds that fits the buffers and
+// every task gets the same number of row BYTES, instead of a full round of maximal tasks plus a
+// straggler round (measured before: warps finished after 15 us on average, the slowest after
+// 43 us, because 2589 13-row tasks were dealt to 2368 warps).
+__device__ __forceinline__ unsigned apply_need(const TableDev& T) {    // weights + accumulated gradient + state
+    return (2u * (unsigned)T.wstride + (unsigned)T.sstride) * 4u;
 }
-// block_task_prefix with ceil(cnt / apply_chunk(table)) tasks per table
-__device__ __forceinline__ void block_apply_prefix(const unsigned* cnt, int n, int* s_prefix, int stride,
-                                                   const TableDev* tab, int use_bulk) {
+__device__ __forceinline__ bool apply_is_bulk(const TableDev& T, int use_bulk) {
+    return use_bulk && T.vec4 && apply_need(T) <= EXB_APPLY_WARP_BUF;
+}
+__device__ __forceinline__ int apply_max_rows(const TableDev& T, int use_bulk) {
+    if (!apply_is_bulk(T, use_bulk)) return 32;
+    return min(32, (int)(EXB_APPLY_WARP_BUF / apply_need(T)));
+}
+// s_prefix[0..n]: task prefix; s_chunk[i]: rows per task of table i; s_cnt[i]: unique rows of table i
+__device__ __forceinline__ void block_apply_prefix(const unsigned* cnt, int n, int* s_prefix, int* s_chunk, int* s_cnt,
+                                                   int stride, const TableDev* tab, int use_bulk) {
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         const int per = (n + 31) / 32;
-        int beg = lane * per, end = min(n, beg + per);
+        const int beg = lane * per, end = min(n, beg + per);
+        unsigned long long bytes = 0;
+        for (int i = beg; i < end; ++i) {
+            const unsigned c = __ldcg(&cnt[(size_t)i * stride]);
+            s_cnt[i] = (int)c;
+            bytes += (unsigned long long)c * apply_need(tab[i]);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        // rounds the phase needs when every task fills a warp buffer; then equal tasks over exactly that many rounds
+        const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+        const unsigned long long rounds = max(1ull, (bytes + nw * EXB_APPLY_WARP_BUF - 1) / (nw * EXB_APPLY_WARP_BUF));
+        const unsigned budget = (unsigned)((bytes + nw * rounds - 1) / (nw * rounds));   // row bytes per task
         int sum = 0;
         for (int i = beg; i < end; ++i) {
-            const int c = apply_chunk(tab[i], use_bulk);
-            sum += (int)((__ldcg(&cnt[(size_t)i * stride]) + (unsigned)c - 1u) / (unsigned)c);
+            const int c = max(1, min(apply_max_rows(tab[i], use_bulk), (int)(budget / apply_need(tab[i])) + 1));
+            s_chunk[i] = c;
+            sum += (s_cnt[i] + c - 1) / c;
         }
         int incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
@@ -398,8 +424,7 @@ __device__ __forceinline__ void block_apply_prefix(const unsigned* cnt, int n, i
         int run = incl - sum;
         for (int i = beg; i < end; ++i) {
             s_prefix[i] = run;
-            const int c = apply_chunk(tab[i], use_bulk);
-            run += (int)((__ldcg(&cnt[(size_t)i * stride]) + (unsigned)c - 1u) / (unsigned)c);
+            run += (s_cnt[i] + s_chunk[i] - 1) / s_chunk[i];
         }
         if (lane == 31) s_prefix[n] = incl;
     }
@@ -666,7 +691,9 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     EXB_STAMP(4);
 
     // ---------------- P5: apply optimizer to every unique row
-    block_apply_prefix(P.ucount, PT, s_prefix, EXB_CTR_STRIDE, S.tab, P.use_bulk);
+    int* s_chunk = s_prefix + 256;     // the combine phase is over: its 1025-entry prefix array is free again
+    int* s_cnt5 = s_prefix + 512;
+    block_apply_prefix(P.ucount, PT, s_prefix, s_chunk, s_cnt5, EXB_CTR_STRIDE, S.tab, P.use_bulk);
     const int ntask5 = s_prefix[PT];
     unsigned n_unique_local = 0;
     unsigned long long* tr = P.trace ? P.trace + (size_t)warp * EXB_TRACE_SLOTS : nullptr;
@@ -675,8 +702,8 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     for (int task = warp; task < ntask5; task += nwarps) {
         const int pt = find_segment(s_prefix, PT, task);
         const TableDev& T = S.tab[pt];
-        const int chunk = apply_chunk(T, P.use_bulk);
-        const unsigned n = __ldcg(&P.ucount[pt * EXB_CTR_STRIDE]);
+        const int chunk = s_chunk[pt];
+        const unsigned n = (unsigned)s_cnt5[pt];
         const unsigned u = lane < chunk ? (unsigned)(task - s_prefix[pt]) * (unsigned)chunk + lane : n;
 #ifdef EXB_PROBE
         const bool probe5 = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
@@ -690,11 +717,11 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
         int flag = 0;
         if (u < n) {
             h = __ldcg(&P.ulist[S.ulist_off[pt] + u]);
-            if (trt && lane == 0) trt[2] = globaltimer_after(h);
+            key = __ldcg(&P.ukeys[S.ulist_off[pt] + u]);
+            if (trt && lane == 0) trt[2] = globaltimer_after(h + key);
             const unsigned long long mo = S.map_off[pt] + h;
-            key = __ldcg(&P.cmap_keys[mo]);
-            cnt = __ldcg(&P.cmap_cnt[mo]);
-            if (trt && lane == 0) trt[3] = globaltimer_after(key + cnt);
+            cnt = (T.opt.kind == OPT_TEST) ? __ldcg(&P.cmap_cnt[mo]) : 1u;   // only the test optimizer uses the count
+            if (trt && lane == 0) trt[3] = globaltimer_after(cnt);
             P.cmap_keys[mo] = EXB_EMPTY_KEY;
             P.cmap_cnt[mo] = 0;
             if (!T.is_hash) {
@@ -728,7 +755,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
         if (probe5) P.stats[23] = globaltimer_ns() + (row & 0) + (cnt & 0);
 #endif
         if (trt && lane == 0) trt[4] = globaltimer_after(row + (unsigned)flag);
-        if (P.use_bulk && T.vec4 && (2 * T.wstride + T.sstride) * 4 <= EXB_APPLY_WARP_BUF) {
+        if (apply_is_bulk(T, P.use_bulk)) {
             apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, chunk, trt);
             if (trt && lane == 0) { __threadfence(); trt[6] = globaltimer_ns(); }
             continue;
