@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 namespace {
@@ -670,6 +671,7 @@ struct ArArgs {
     unsigned* flags[8];     // every rank's flag array [8]
     unsigned* epoch;        // local
     unsigned* gcount;       // local: CTA arrival counter
+    unsigned long long* stamps;   // local, optional: %globaltimer of CTA 0 [start, ready, reduced, landed, done]
     int* status;
     long long n;
     int W, rank;
@@ -704,8 +706,11 @@ __global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, DenseOptArg
     __shared__ int s_last;
     __shared__ float opt_tile[32][33];
     const unsigned e0 = *(volatile unsigned*)a.epoch;
+#define AR_STAMP(i) do { if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); a.stamps[i] = _t; } } while (0)
+    AR_STAMP(0);
     if (blockIdx.x == 0) ar_signal(a, e0 + 1);     // earlier kernels of this stream wrote the gradients
     ar_wait(a, e0 + 1);
+    AR_STAMP(1);
     const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
     const long long lo = per * a.rank, hi = min(a.n, lo + per);
     for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
@@ -723,6 +728,7 @@ __global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, DenseOptArg
             if (r < a.W) __stcg(reinterpret_cast<float4*>(a.buf[r] + i), s);             // peer stores
     }
     __syncthreads();
+    AR_STAMP(2);
     if (threadIdx.x == 0) {
         asm volatile("fence.acq_rel.sys;" ::: "memory");     // cumulative over the CTA's peer stores
         s_last = atomicAdd(a.gcount, 1u) == gridDim.x - 1;
@@ -738,8 +744,11 @@ __global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, DenseOptArg
         ar_signal(a, e0 + 2);
     }
     ar_wait(a, e0 + 2);
+    AR_STAMP(3);
     if (o.theta == nullptr) return;
     dense_opt_step(o, opt_tile);     // o.grad == a.buf[a.rank]: identical on every rank now
+    AR_STAMP(4);
+#undef AR_STAMP
 }
 
 }  // namespace
@@ -831,6 +840,7 @@ int exb_allreduce_adagrad(const uint64_t* bufs, const uint64_t* flags, uint64_t 
     ArArgs a;
     for (int i = 0; i < 8; ++i) { a.buf[i] = i < W ? (float*)bufs[i] : nullptr; a.flags[i] = i < W ? (unsigned*)flags[i] : nullptr; }
     a.epoch = (unsigned*)epoch; a.gcount = (unsigned*)gcount; a.status = (int*)status; a.n = n; a.W = W; a.rank = rank;
+    a.stamps = (unsigned long long*)(gcount + 1024);   // flag block + 4096: phase clock of CTA 0
     if (n % 4) { g_dense_err = "allreduce: n must be a multiple of 4"; return -1; }
     DenseOptArgs o;
     memset(&o, 0, sizeof(o));
@@ -838,8 +848,12 @@ int exb_allreduce_adagrad(const uint64_t* bufs, const uint64_t* flags, uint64_t 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ctas < 1) ctas = 1;
-    if (ctas > sms) ctas = sms;             // CTAs wait on each other: keep the grid resident
+    // CTAs wait on each other (flag polls, arrival counter): the grid must be resident. Up to 4 CTAs per
+    // SM: the optimizer phase walks 32x32 weight tiles grid-strided and wants the parallelism.
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_ar_fused_kernel, 256, 0);
+    const int resident = sms * std::max(1, std::min(occ, 4));
+    if (ctas < 1 || ctas > resident) ctas = resident;
     cudaError_t e = exb::launch_pdl(exb_ar_fused_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, a, o);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;

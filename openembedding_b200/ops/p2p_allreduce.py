@@ -30,7 +30,7 @@ class P2PAllReduce:
     tensor through two local copies. ``__call__(theta, accum, lr, eps)`` fuses the dense
     Adagrad step behind the reduction (one launch)."""
 
-    def __init__(self, ctx, flat, ctas=148):
+    def __init__(self, ctx, flat, ctas=0):
         import torch.distributed as dist
         self.ctx, self.W, self.rank = ctx, ctx.world, ctx.rank
         self.lib = _native.cuda()
@@ -79,6 +79,13 @@ class P2PAllReduce:
             raise RuntimeError("exb_allreduce_adagrad: " + self.lib.exb_dense_last_error().decode())
         if self.flat is not None:
             self.flat.copy_(self.local, non_blocking=True)
+
+    def phases_us(self):
+        """in-kernel phase clock of the last call (CTA 0): wait for peers' gradients, reduce+broadcast,
+        wait for peers' stores, optimizer"""
+        t = tensor_from_ptr(self.flag_ptr + 4096, 10, self.dev, dtype=torch.int32).cpu().view(torch.int64).tolist()
+        names = ["wait_ready", "reduce_bcast", "wait_landed", "optimizer"]
+        return {n: (t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names) if t[i + 1] and t[i]}
 
     def status(self):
         t = tensor_from_ptr(self.flag_ptr + 2048, 1, self.dev, dtype=torch.int32)

@@ -59,6 +59,8 @@ st = ctx.backend.engine.status()[1]
 print(line, flush=True)
 if ctx.rank == 0 and st:
     print("push phases (last step, us):", st.get("last_push_update_us"), flush=True)
+    if m._ar is not None:
+        print("all-reduce phases (last step, us):", m._ar.phases_us(), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
