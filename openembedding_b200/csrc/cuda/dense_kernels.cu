@@ -681,15 +681,27 @@ __device__ __forceinline__ void ar_signal(const ArArgs& a, unsigned e) {   // th
     if ((int)threadIdx.x < a.W)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.flags[threadIdx.x][a.rank]), "r"(e) : "memory");
 }
+// ONE polling thread per CTA reads the whole local flag row (<= 8 words) with two 16-byte loads and
+// backs off between polls: W threads x several hundred CTAs re-reading one L2 line every ~0.5 us
+// saturated its slice -- CTAs noticed a flag up to 14 us after it had been set (per-CTA stamps,
+// profiles/sparse_path.md).
+__device__ __forceinline__ bool ar_flags_reached(const unsigned* row, int W, unsigned e) {
+    unsigned v[8];
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(row) : "memory");
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(row + 4) : "memory");
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ok = ok && (i >= W || (int)(v[i] - e) >= 0);
+    return ok;
+}
 __device__ __forceinline__ void ar_wait(const ArArgs& a, unsigned e) {     // every CTA
-    if ((int)threadIdx.x < a.W) {
+    if (threadIdx.x == 0) {
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (unsigned it = 0;; ++it) {
-            unsigned v;
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&a.flags[a.rank][threadIdx.x]) : "memory");
-            if ((int)(v - e) >= 0) break;
-            __nanosleep(20);
+        unsigned ns = 32;
+        for (unsigned it = 0; !ar_flags_reached(a.flags[a.rank], a.W, e); ++it) {
+            __nanosleep(ns);
+            if (ns < 256) ns += 32;
             if ((it & 255u) == 255u) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                 if (t1 - t0 > 4000000000ull) { atomicCAS(a.status, 0, 2); break; }
@@ -708,40 +720,63 @@ __global__ void __launch_bounds__(256) exb_ar_fused_kernel(ArArgs a, DenseOptArg
     const unsigned e0 = *(volatile unsigned*)a.epoch;
 #define AR_STAMP(i) do { if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); a.stamps[i] = _t; } } while (0)
     AR_STAMP(0);
+#define AR_CTA_STAMP(i) do { if (a.stamps && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); a.stamps[16 + 4 * blockIdx.x + (i)] = _t; } } while (0)
+    AR_CTA_STAMP(0);
     if (blockIdx.x == 0) ar_signal(a, e0 + 1);     // earlier kernels of this stream wrote the gradients
     ar_wait(a, e0 + 1);
     AR_STAMP(1);
+    AR_CTA_STAMP(1);
     const long long per = ((a.n + a.W - 1) / a.W + 3) & ~3ll;
     const long long lo = per * a.rank, hi = min(a.n, lo + per);
-    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi;
-         i += (long long)gridDim.x * blockDim.x * 4) {
-        float4 v[8];
+    // two float4 per thread and iteration: 2 W independent peer loads in flight before the first use
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const bool two = i2 < hi;
+        float4 v[8], u[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < a.W) v[r] = __ldcg(reinterpret_cast<const float4*>(a.buf[r] + i));   // peer loads over NVLink
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.W) {
+                v[r] = __ldcg(reinterpret_cast<const float4*>(a.buf[r] + i));   // peer loads over NVLink
+                if (two) u[r] = __ldcg(reinterpret_cast<const float4*>(a.buf[r] + i2));
+            }
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < a.W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+            if (r < a.W) {
+                s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w;
+                if (two) { t.x += u[r].x; t.y += u[r].y; t.z += u[r].z; t.w += u[r].w; }
+            }
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < a.W) __stcg(reinterpret_cast<float4*>(a.buf[r] + i), s);             // peer stores
+            if (r < a.W) {
+                __stcg(reinterpret_cast<float4*>(a.buf[r] + i), s);             // peer stores
+                if (two) __stcg(reinterpret_cast<float4*>(a.buf[r] + i2), t);
+            }
     }
     __syncthreads();
     AR_STAMP(2);
+    AR_CTA_STAMP(2);
     if (threadIdx.x == 0) {
-        asm volatile("fence.acq_rel.sys;" ::: "memory");     // cumulative over the CTA's peer stores
+        // gpu-scope release of the CTA's (peer) stores into the arrival count; the LAST CTA's
+        // st.release.sys below is cumulative over everything it acquired through that count, so only
+        // one system-scope fence sits on the critical path (a MEMBAR.SYS with NVLink stores in flight
+        // was measured at 15-20 us at 8 GPUs: profiles/sparse_path.md)
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         s_last = atomicAdd(a.gcount, 1u) == gridDim.x - 1;
     }
+    AR_CTA_STAMP(3);
     __syncthreads();
     if (s_last) {
         if (threadIdx.x == 0) {
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
             *(volatile unsigned*)a.gcount = 0;
             *(volatile unsigned*)a.epoch = e0 + 2;
+            if (a.stamps) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); a.stamps[5] = _t; }
         }
         __syncthreads();
         ar_signal(a, e0 + 2);
+        if (a.stamps && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); a.stamps[6] = _t; }
     }
     ar_wait(a, e0 + 2);
     AR_STAMP(3);
@@ -853,7 +888,8 @@ int exb_allreduce_adagrad(const uint64_t* bufs, const uint64_t* flags, uint64_t 
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exb_ar_fused_kernel, 256, 0);
     const int resident = sms * std::max(1, std::min(occ, 4));
-    if (ctas < 1 || ctas > resident) ctas = resident;
+    if (ctas < 1) ctas = opt_args ? resident : sms;
+    if (ctas > resident) ctas = resident;
     cudaError_t e = exb::launch_pdl(exb_ar_fused_kernel, dim3(ctas), dim3(256), 0, (cudaStream_t)stream, a, o);
     if (e != cudaSuccess) { g_dense_err = cudaGetErrorString(e); return -1; }
     return 0;

@@ -212,9 +212,10 @@ __device__ __forceinline__ void grid_barrier(const PlanDev& P, bool sys_scope, M
             if (sys_scope) fence_acq_rel_sys(); else fence_acq_rel_gpu();
             atomicAdd(&P.gbar[0], 1u);
             unsigned long long t0 = globaltimer_ns();
-            unsigned it = 0;
+            unsigned it = 0, ns = 32;
             while (ld_relaxed_gpu_u32(&P.gbar[1]) == gen) {
-                __nanosleep(20);
+                __nanosleep(ns);             // growing back-off: ~300 CTAs poll this one line
+                if (ns < 128) ns += 32;
                 if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                     set_error(P.status, EXB_ERR_TIMEOUT_GRID);
                     break;
@@ -259,12 +260,23 @@ __device__ __forceinline__ void peer_barrier(const PlanDev& P, bool wait = true)
 // Every CTA of a kernel that reads peer shards: wait until all peers have signalled the
 // epoch this rank has reached (their last update is complete and visible).
 __device__ __forceinline__ void peer_wait(const PlanDev& P) {
-    if ((int)threadIdx.x < P.W) {
+    // one polling thread per CTA, whole flag row per poll (two 16-byte loads), growing back-off: several
+    // hundred CTAs x W threads re-reading one L2 line saturate its slice and delay everybody
+    if (threadIdx.x == 0) {
         const unsigned e = *(volatile unsigned*)P.epoch;
+        const unsigned* row = P.flags[P.rank];
         unsigned long long t0 = globaltimer_ns();
-        unsigned it = 0;
-        while ((int)(ld_relaxed_sys_u32(&P.flags[P.rank][threadIdx.x]) - e) < 0) {
-            __nanosleep(20);
+        unsigned it = 0, ns = 32;
+        for (;;) {
+            unsigned v[8];
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(row) : "memory");
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(row + 4) : "memory");
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ok = ok && (i >= P.W || (int)(v[i] - e) >= 0);
+            if (ok) break;
+            __nanosleep(ns);
+            if (ns < 256) ns += 32;
             if ((++it & 255u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
                 set_error(P.status, EXB_ERR_TIMEOUT_PEER);
                 break;

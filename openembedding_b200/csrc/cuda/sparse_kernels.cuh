@@ -643,7 +643,9 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     EXB_STAMP(1);
     if (W > 1) {
         // ---------------- B1: publish counts, cross-GPU barrier
-        grid_barrier(P, true, [&]() {
+        // CTAs arrive with a gpu-scope release; the one system-scope release (cumulative over the whole
+        // grid's inbox stores) is the flag store in peer_barrier
+        grid_barrier(P, false, [&]() {
             for (int i = threadIdx.x; i < W * PT; i += blockDim.x) {
                 int o = i / PT, pt = i - o * PT;
                 unsigned c = __ldcg(&P.send_cnt[i * EXB_CTR_STRIDE]);

@@ -324,11 +324,12 @@ class FusedCTR:
                 self._mark("push_update")
             # Adagrad + bf16 weight refresh + gradient clearing: one kernel (world > 1: behind the all-reduce,
             # in the same kernel)
+            # world > 1: the all-reduce runs on one CTA per SM (every CTA polls peer flags); the optimizer kernel
+            # is chained behind it with a programmatic dependent launch instead of sharing its grid
             if self._ar is not None:
-                self._ar(self._opt_args)
-                self._mark("allreduce+optimizer")
-            else:
-                _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
+                self._ar()
+                self._mark("allreduce")
+            _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
             self._mark("optimizer")
             if forked:
                 torch.cuda.current_stream(self.dev).wait_event(self._ev_join)
@@ -343,7 +344,7 @@ class FusedCTR:
         prep = 1 if (self.mn_major and 128 % self.Dp == 0) else 2
         head = 1 if (self.mn_major and self.Hp[-1] <= 512) else 2
         n = 1 + prep + L + head + L + L + (1 if self.nc else 0) + 1 + 1   # pull prep fwd head dX dW cache push optimizer
-        return n     # world > 1: the fused all-reduce+Adagrad kernel replaces the Adagrad launch
+        return n + (1 if self._ar is not None else 0)
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)
     def reference(self, ids, dense, labels):

@@ -83,9 +83,20 @@ class P2PAllReduce:
     def phases_us(self):
         """in-kernel phase clock of the last call (CTA 0): wait for peers' gradients, reduce+broadcast,
         wait for peers' stores, optimizer"""
-        t = tensor_from_ptr(self.flag_ptr + 4096, 10, self.dev, dtype=torch.int32).cpu().view(torch.int64).tolist()
+        t = tensor_from_ptr(self.flag_ptr + 4096, 14, self.dev, dtype=torch.int32).cpu().view(torch.int64).tolist()
         names = ["wait_ready", "reduce_bcast", "wait_landed", "optimizer"]
-        return {n: (t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names) if t[i + 1] and t[i]}
+        out = {n: (t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names) if t[i + 1] and t[i]}
+        c = tensor_from_ptr(self.flag_ptr + 4096 + 128, 2 * 4 * 1200, self.dev, dtype=torch.int32).cpu().view(torch.int64).view(-1, 4)
+        c = c[c[:, 0] > 0]
+        if c.numel():
+            t0 = int(c[:, 0].min())
+            for k, nm in enumerate(["cta_start", "cta_ready", "cta_reduced", "cta_arrived"]):
+                col = (c[:, k] - t0).double() / 1e3
+                out[nm] = "min %.1f mean %.1f max %.1f (argmax cta %d of %d)" % (col.min(), col.mean(), col.max(), int(col.argmax()), c.shape[0])
+        if t[5] and t[2]:
+            out["last_cta_arrived_after_reduce"] = (t[5] - t[2]) / 1e3
+            out["signal_issue"] = (t[6] - t[5]) / 1e3
+        return out
 
     def status(self):
         t = tensor_from_ptr(self.flag_ptr + 2048, 1, self.dev, dtype=torch.int32)
