@@ -29,6 +29,7 @@ from torch import nn
 from . import checkpoint as _ckpt
 from . import flags  # noqa: F401  (re-export like `from openembedding import *`)
 from .config import HASH_KEY_RANGE, normalize_initializer, normalize_optimizer, str_dict
+from .utils import timers
 from .context import get_context
 
 _HASH_KEY_RANGE = HASH_KEY_RANGE
@@ -195,12 +196,17 @@ class Variable:
         flat = indices.reshape(-1)
         if self.tier is not None:
             self.tier.prefetch(flat)          # promote missing rows from the host store into HBM
-        rows = ctx.backend.pull(self.variable, flat)
+        with timers.vtimer(1, "client", "pull_weights", cuda=ctx.device.type == "cuda"):
+            rows = ctx.backend.pull(self.variable, flat)
+        if timers.enabled:
+            timers.add_count("pull_indices", flat.numel())
+            timers.add_count("pull_unique", int(torch.unique(flat).numel()))
         return rows.reshape(tuple(indices.shape) + tuple(self._shape[1:])).to(self._tdtype)
 
     def _push(self, indices, grads):
         ctx = get_context()
-        ctx.backend.push(self.variable, indices.reshape(-1), grads.reshape(-1, self.variable.dim))
+        with timers.vtimer(1, "client", "push_gradients", cuda=ctx.device.type == "cuda"):
+            ctx.backend.push(self.variable, indices.reshape(-1), grads.reshape(-1, self.variable.dim))
         if self.tier is not None:
             self.tier.mark_updated(indices)
 
@@ -248,7 +254,9 @@ class Variable:
     def update_weights(self, fake_grad=None):
         if self.sparse_as_dense:
             raise ValueError("no need update weights for sparse as dense.")
-        get_context().backend.update([self.variable])
+        ctx = get_context()
+        with timers.vtimer(1, "client", "update_weights", cuda=ctx.device.type == "cuda"):
+            ctx.backend.update([self.variable])
         if self.tier is not None:
             self.tier.next_work()
 
@@ -319,8 +327,27 @@ class Embedding(nn.Module):
                                      graph_var=self.embeddings, host_tier_rows=host_tier_rows)
         self.built = True
 
-    def forward(self, inputs):
+    def forward(self, inputs, offsets=None, per_sample_weights=None, mode="sum"):
+        """``inputs``: int tensor of any shape -> ``inputs.shape + (output_dim,)``.
+
+        Multi-hot / ragged features (the reference reaches them through
+        ``tf.ragged.map_flat_values(embedding, ragged_ids)``, exb.py:388-443): pass the flat
+        values as a 1-D ``inputs`` plus ``offsets`` (start of every bag, like
+        ``nn.EmbeddingBag``) and get one pooled row per bag (``mode`` sum | mean | max is
+        applied on this rank after ONE pull of the flat ids, so duplicated ids inside a batch
+        travel once). A ``torch.nested`` tensor is accepted too and returns a nested result."""
+        if offsets is None and getattr(inputs, "is_nested", False):
+            parts = inputs.unbind()
+            flat = torch.cat([p.reshape(-1) for p in parts])
+            rows = self.variable.sparse_read(flat)
+            out, o = [], 0
+            for p in parts:
+                out.append(rows[o:o + p.numel()].reshape(tuple(p.shape) + (self.output_dim,)))
+                o += p.numel()
+            return torch.nested.nested_tensor(out)
         out = self.variable.sparse_read(inputs)
+        if offsets is not None:
+            out = _pool_bags(out, offsets.to(out.device), per_sample_weights, mode)
         if self.activity_regularizer is not None and self.training:
             self.activity_loss = self.activity_regularizer(out)
         return out
@@ -328,6 +355,28 @@ class Embedding(nn.Module):
     def extra_repr(self):
         v = "2**63" if self.input_dim >= _HASH_KEY_RANGE else str(self.input_dim)
         return "%s, %d, sparse_as_dense=%s" % (v, self.output_dim, self.sparse_as_dense)
+
+
+def _pool_bags(rows, offsets, per_sample_weights=None, mode="sum"):
+    """rows [n, D] of the flat ids, offsets [bags] -> [bags, D] (differentiable)."""
+    n, bags = rows.shape[0], offsets.numel()
+    if per_sample_weights is not None:
+        if mode != "sum":
+            raise ValueError("per_sample_weights needs mode='sum'")
+        rows = rows * per_sample_weights.to(rows.device, rows.dtype).reshape(-1, 1)
+    ends = torch.cat([offsets[1:], torch.tensor([n], device=offsets.device, dtype=offsets.dtype)])
+    lens = (ends - offsets).clamp_(min=0)
+    bag_of = torch.repeat_interleave(torch.arange(bags, device=rows.device), lens.to(rows.device))
+    if mode in ("sum", "mean"):
+        out = torch.zeros((bags, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, bag_of, rows)
+        if mode == "mean":
+            out = out / lens.clamp(min=1).to(rows.dtype).reshape(-1, 1)
+        return out
+    if mode == "max":
+        out = torch.full((bags, rows.shape[1]), float("-inf"), dtype=rows.dtype, device=rows.device)
+        out = out.scatter_reduce(0, bag_of.reshape(-1, 1).expand_as(rows), rows, reduce="amax", include_self=True)
+        return torch.where(torch.isinf(out), torch.zeros_like(out), out)
+    raise ValueError("mode must be sum, mean or max")
 
 
 # --------------------------------------------------------------------------- optimizers

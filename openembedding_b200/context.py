@@ -57,6 +57,13 @@ class Context:
         self.storages = []
         self.variables = []          # VarMeta by variable_id
         self.tracks = {}             # id(graph_var) -> api.Variable
+        # server.report_interval > 0: timers/counters on, rank 0 prints the table periodically
+        # (reference: WorkerContext.cpp:24-41, 140-163)
+        self.monitor = None
+        interval = float(self.env["server"]["report_interval"])
+        if interval > 0:
+            from .utils import timers
+            self.monitor = timers.Monitor(self, interval).start()
         atexit.register(self.finalize)
 
     # ---- control plane (reference: client/Communication.h:12-73)
@@ -112,6 +119,9 @@ class Context:
 
     def finalize(self):
         global _context
+        if getattr(self, "monitor", None) is not None:
+            self.monitor.stop()
+            self.monitor = None
         if getattr(self, "backend", None) is not None:
             try:
                 self.backend.close()

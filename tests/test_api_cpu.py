@@ -128,3 +128,29 @@ def test_pulling_prefetches_ids(cpu_context):
     got = list(embed.pulling(data, m))
     assert len(got) == 5 and all(torch.equal(a[0]["C1"], b[0]["C1"]) for a, b in zip(got, data))
     assert len(list(embed.pulling(data, m, steps=3))) == 3
+
+
+def test_embedding_multi_hot_bags(cpu_context):
+    """ragged / multi-hot ids: flat values + offsets (EmbeddingBag semantics) and nested tensors"""
+    import openembedding_b200.torch as embed
+    emb = embed.Embedding(50, 4, embeddings_initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+    flat = torch.tensor([3, 7, 7, 1, 9, 3])
+    offsets = torch.tensor([0, 2, 2, 5])          # bags: [3,7] [] [7,1,9] [3]
+    rows = emb(flat).detach()
+    out = emb(flat, offsets=offsets)
+    ref = torch.stack([rows[0:2].sum(0), torch.zeros(4), rows[2:5].sum(0), rows[5:6].sum(0)])
+    assert torch.allclose(out, ref)
+    assert torch.allclose(emb(flat, offsets=offsets, mode="mean")[2], rows[2:5].mean(0))
+    assert torch.allclose(emb(flat, offsets=offsets, mode="max")[0], rows[0:2].max(0).values)
+    w = torch.tensor([1.0, 2.0, 0.5, 1.0, 1.0, 3.0])
+    assert torch.allclose(emb(flat, offsets=offsets, per_sample_weights=w)[3], 3.0 * rows[5])
+    # gradients flow back to the rows of the bag (duplicates summed by the server-side reduce)
+    opt = embed.distributed_optimizer(torch.optim.SGD(emb.parameters(), lr=1.0))
+    before = emb(torch.tensor([7])).detach().clone()
+    loss = emb(flat, offsets=offsets).sum()
+    opt.zero_grad(); loss.backward(); opt.step()
+    after = emb(torch.tensor([7])).detach()
+    assert torch.allclose(after, before - 2.0)    # id 7 appears twice, d(loss)/d(row) = 1 each
+    nt = torch.nested.nested_tensor([torch.tensor([1, 2, 3]), torch.tensor([4])])
+    res = emb(nt)
+    assert res.is_nested and [tuple(t.shape) for t in res.unbind()] == [(3, 4), (1, 4)]

@@ -113,3 +113,32 @@ def test_masterd_entry():
     finally:
         p.terminate()
         p.wait(timeout=10)
+
+
+def test_report_interval_enables_timers_and_counters(capsys):
+    """server.report_interval > 0 -> vtimers / pull_indices / pull_unique are collected, Monitor prints them"""
+    import openembedding_b200 as oe
+    import openembedding_b200.torch as embed
+    from openembedding_b200.context import get_context, reset_context
+    from openembedding_b200.utils import timers
+    reset_context()
+    timers.reset()
+    oe.flags.device = "cpu"
+    old = oe.flags.config
+    oe.flags.config = '{"server": {"report_interval": 1}}'
+    try:
+        v = embed.Variable(shape=(100, 4), name="v", num_shards=1)
+        ids = torch.tensor([1, 2, 2, 3, 3, 3])
+        v.sparse_read(ids)
+        v.push_gradients(ids, torch.ones(6, 4))
+        v.update_weights()
+        snap = timers.snapshot(get_context())
+        assert snap["counters"]["pull_indices"] >= 6 and snap["counters"]["pull_unique"] >= 3
+        assert "client.pull_weights" in snap["timers"] and "client.update_weights" in snap["timers"]
+        time.sleep(1.4)
+        assert "client.pull_weights" in capsys.readouterr().out          # the Monitor thread printed the table
+    finally:
+        oe.flags.config = old
+        reset_context()
+        timers.enable(False)
+        timers.reset()
