@@ -455,7 +455,7 @@ def _DistributedOptimizer(T):
                 for v in tracked:
                     if v.tier is not None:
                         v.tier.next_work()
-            ctx.model_version += 1
+            ctx.step_done()
             try:
                 return super().step(closure)
             finally:

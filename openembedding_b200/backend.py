@@ -380,6 +380,18 @@ class CudaBackend:
     def table_kind(self, meta):
         return "hash" if meta.is_hash else "array"
 
+    grow_interval, max_load, _steps = 64, 0.5, 0
+
+    def tick(self, n=1):
+        """per training step. The reference's hash tables grow on insert (EasyHashMap rehash at load 1/2);
+        here a full shard is an error code of the update kernel, so every `grow_interval` steps the
+        occupancy is read back and shards above `max_load` are doubled (rehash_kernel) on all ranks."""
+        before = self._steps
+        self._steps += n
+        if self.grow_interval > 0 and before // self.grow_interval != self._steps // self.grow_interval:
+            if any(m.is_hash and m.allocated for m in self.vars):
+                self.maybe_grow(self.max_load)
+
     def maybe_grow(self, load_factor=0.5):
         """Collective: grow hash shards whose load exceeds `load_factor` (all ranks agree)."""
         import torch.distributed as dist

@@ -254,6 +254,7 @@ _ENV_DEFAULTS = {
         "update_early_return": True,
         # B200 engine additions
         "hash_table_reserve": 1 << 20, "host_tier_root_path": "", "deterministic": False,
+        "hash_table_grow_interval": 64, "hash_table_max_load": 0.5,
     },
 }
 _ENV_CHECKS = {

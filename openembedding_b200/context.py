@@ -47,6 +47,8 @@ class Context:
             local_rank = int(os.environ.get("LOCAL_RANK", self.rank % max(1, torch.cuda.device_count())))
             self.backend = CudaBackend(self.rank, self.world, local_rank, group=None)
             self.backend.hash_reserve = int(self.env["server"]["hash_table_reserve"])
+            self.backend.grow_interval = int(self.env["server"]["hash_table_grow_interval"])
+            self.backend.max_load = float(self.env["server"]["hash_table_max_load"])
         else:
             if self.dist_on and dist.get_backend() != "gloo":
                 self.group = dist.new_group(backend="gloo")
@@ -113,6 +115,14 @@ class Context:
     def set_optimizer(self, meta, config):
         meta.optimizer = normalize_optimizer(config)
         self.backend.set_optimizer(meta, meta.optimizer)
+
+    def step_done(self, n=1):
+        """once per training step: advances the model version and lets the backend do its periodic
+        maintenance (hash shards above the load factor are grown, collectively)"""
+        self.model_version += n
+        tick = getattr(self.backend, "tick", None)
+        if tick is not None:
+            tick(n)
 
     def model_sign(self):
         return "%s-%d" % (self.model_uuid, int(self.model_version))

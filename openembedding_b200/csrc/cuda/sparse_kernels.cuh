@@ -573,9 +573,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     // stats[8..15] (read by utils.timers; the in-kernel equivalent of the reference's VTIMER)
 #define EXB_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[8 + (i)] = globaltimer_ns(); } while (0)
     EXB_STAMP(0);
-#ifdef EXB_PROBE
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[21] = globaltimer_ns();
-#endif
 
     // ---------------- P1: dispatch (remote ids -> owner inbox, local ids -> combine map)
     for (int task = warp; task < P.num_tasks; task += nwarps) {
@@ -595,22 +592,11 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
         const float* src = grads + (size_t)b * P.io_stride + S.feat_off[f];
         float* dst = nullptr;
         int mode = 0;
-#ifdef EXB_PROBE
-        const bool probe = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
-        if (probe) { P.stats[16] = globaltimer_ns(); P.stats[17] = id; }
-#endif
         {
             unsigned h = cmap_insert_warp(P, S, pt, id, owner == rank, lane);
-#ifdef EXB_PROBE
-            if (probe) { P.stats[18] = globaltimer_ns() + (h & 0); }
-#endif
             if (h != 0xFFFFFFFFu) {
                 unsigned old = atomicAdd(&P.cmap_cnt[S.map_off[pt] + h], 1u);
-#ifdef EXB_PROBE
-                if (probe) { P.stats[19] = globaltimer_ns() + (old & 0); }
-#else
                 (void)old;
-#endif
                 dst = P.acc + S.acc_off[pt] + (unsigned long long)h * T.wstride;
                 mode = 1;
             }
@@ -635,9 +621,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             }
         }
         move_rows_dispatch(T, src, dst, mode, lane);
-#ifdef EXB_PROBE
-        if (probe) { __threadfence(); P.stats[20] = globaltimer_ns(); }
-#endif
     }
 
     EXB_STAMP(1);
@@ -707,10 +690,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
         const int chunk = s_chunk[pt];
         const unsigned n = (unsigned)s_cnt5[pt];
         const unsigned u = lane < chunk ? (unsigned)(task - s_prefix[pt]) * (unsigned)chunk + lane : n;
-#ifdef EXB_PROBE
-        const bool probe5 = (blockIdx.x == 0 && threadIdx.x == 0 && task == warp);
-        if (probe5) P.stats[22] = globaltimer_ns();
-#endif
         unsigned long long* trt = (tr && trk + 8 <= EXB_TRACE_SLOTS) ? tr + trk : nullptr;
         trk += 8;
         if (trt && lane == 0) { trt[0] = (unsigned long long)task | ((unsigned long long)pt << 32); trt[1] = globaltimer_after(n); }
@@ -753,9 +732,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             if (nm && lane == __ffs(nm) - 1) atomicAdd(T.size_ctr, (unsigned long long)__popc(nm));
         }
         float* accbase = P.acc + S.acc_off[pt];
-#ifdef EXB_PROBE
-        if (probe5) P.stats[23] = globaltimer_ns() + (row & 0) + (cnt & 0);
-#endif
         if (trt && lane == 0) trt[4] = globaltimer_after(row + (unsigned)flag);
         if (apply_is_bulk(T, P.use_bulk)) {
             apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, chunk, trt);
@@ -770,9 +746,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             case 16: apply_rows<16>(T, P, accbase, key, row, h, cnt, flag, lane); break;
             default: apply_rows<32>(T, P, accbase, key, row, h, cnt, flag, lane); break;
         }
-#ifdef EXB_PROBE
-        if (probe5) { __threadfence(); P.stats[24] = globaltimer_ns(); }
-#endif
     }
     n_unique_local = __reduce_add_sync(0xffffffffu, n_unique_local);
     if (lane == 0 && n_unique_local) atomicAdd(&P.stats[2], (unsigned long long)n_unique_local);

@@ -404,7 +404,9 @@ class FusedTrainer:
 
     def step(self, ids, dense, labels):
         if not self.use_graph:
-            return self.m.forward_backward(ids, dense, labels)
+            loss = self.m.forward_backward(ids, dense, labels)
+            self.ctx.step_done()
+            return loss
         if self.graph is None:
             self._capture(ids, dense, labels)
         s = self._static
@@ -413,6 +415,7 @@ class FusedTrainer:
             s["dense"].copy_(dense, non_blocking=True)
             s["labels"].copy_(labels, non_blocking=True)
         self.graph.replay()
+        self.ctx.step_done()
         return s["loss"]
 
     def _capture(self, ids, dense, labels):

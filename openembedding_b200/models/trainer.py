@@ -79,7 +79,9 @@ class Trainer:
     def step(self, ids, dense, labels):
         """eager or graph-replayed step on device tensors"""
         if not self.use_graph:
-            return self._device_step(ids, dense, labels)
+            loss = self._device_step(ids, dense, labels)
+            self.ctx.step_done()
+            return loss
         if self.graph is None:
             self._capture(ids, dense, labels)
         s = self._static
@@ -88,6 +90,7 @@ class Trainer:
             s["dense"].copy_(dense, non_blocking=True)
             s["labels"].copy_(labels, non_blocking=True)
         self.graph.replay()
+        self.ctx.step_done()
         return s["loss"]
 
     def _capture(self, ids, dense, labels):

@@ -103,3 +103,36 @@ def test_api_embedding_checkpoint_roundtrip(cuda_context):
     assert isinstance(plain.e, torch.nn.Embedding) and plain.e.weight.shape == (5000, 12)
     assert torch.allclose(plain.e.weight[x.cpu()], before_e.cpu())
     ctx.backend.engine.check()
+
+
+def test_hash_table_grows_automatically():
+    """a hashed Embedding whose shard starts tiny keeps training: the periodic maintenance tick doubles the
+    shard before it fills up (reference: EasyHashMap rehash on insert)"""
+    import openembedding_b200 as oe
+    import openembedding_b200.torch as embed
+    from openembedding_b200.context import get_context, reset_context
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    reset_context()
+    old_dev, old_cfg = oe.flags.device, oe.flags.config
+    oe.flags.device = "cuda"
+    oe.flags.config = '{"server": {"hash_table_reserve": 256, "hash_table_grow_interval": 1}}'
+    try:
+        ctx = get_context()
+        emb = embed.Embedding(-1, 8, embeddings_initializer={"category": "constant", "value": 0.0})
+        opt = embed.distributed_optimizer(torch.optim.SGD(emb.parameters(), lr=1.0))
+        seen = set()
+        for step in range(12):
+            ids = torch.arange(step * 100, step * 100 + 100, device=ctx.device) * 7919 + 13
+            seen.update(ids.tolist())
+            loss = emb(ids).sum()
+            opt.zero_grad(); loss.backward(); opt.step()
+        ctx.backend.engine.check()
+        meta = emb.variable.variable
+        assert ctx.backend.engine.table_size(meta.handle) == len(seen) == 1200
+        assert ctx.backend.engine.table_info(meta.handle)["rows"] >= 2 * 1200     # grew from 256 slots
+        probe = torch.tensor(sorted(seen)[:50], device=ctx.device)
+        assert torch.allclose(emb(probe), torch.full((50, 8), -1.0, device=ctx.device))
+    finally:
+        oe.flags.device, oe.flags.config = old_dev, old_cfg
+        reset_context()
