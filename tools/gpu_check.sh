@@ -1,5 +1,6 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/ -m gpu -x -q > gpurun_out/pytest_gpu16.log 2>&1; tail -3 gpurun_out/pytest_gpu16.log
-timeout 300 python bench.py --steps 200 --warmup 20 2>&1 | tail -1 > gpurun_out/bench_v16.log
-python -c "import json; d=json.loads(open('gpurun_out/bench_v16.log').read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['final_loss'], d.get('push_update_phases_us'), d['gpu_launches'], d['clocks'])"
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 600 python -m pytest tests/ -m gpu -x -q > gpurun_out/pytest_gpu17.log 2>&1; tail -3 gpurun_out/pytest_gpu17.log
+timeout 200 python bench.py --steps 200 --warmup 20 2>&1 | tail -1 > gpurun_out/bench_v17.log
+python -c "import json; d=json.loads(open('gpurun_out/bench_v17.log').read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['final_loss'])"
+timeout 200 ncu --set full --import-source on --clock-control none -k regex:gemm_tcgen05 -s 30 -c 9 -f -o gpurun_out/prof_gemm python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_gemm.log 2>&1
+ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/gemm_raw.csv 2>/dev/null; ls -la gpurun_out/prof_gemm.ncu-rep | cut -c1-80
