@@ -142,3 +142,44 @@ def test_report_interval_enables_timers_and_counters(capsys):
         reset_context()
         timers.enable(False)
         timers.reset()
+
+
+def test_checkpoint_through_hdfs_pipe(cpu_context, tmp_path, monkeypatch):
+    """hdfs:// models are staged through `hdfs dfs -put/-get` (reference: ShellUtility pipes). A fake `hdfs`
+    executable that maps hdfs://nn/<p> onto a local directory stands in for the cluster."""
+    import stat
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    root = tmp_path / "fake_hdfs"
+    root.mkdir()
+    fake = tmp_path / "hdfs"
+    fake.write_text("""#!/bin/bash
+# usage: hdfs dfs -mkdir -p P | -put -f SRC... P | -get P/* DST | -test -e P
+ROOT="%s"
+map() { echo "$ROOT/${1#hdfs://nn/}"; }
+shift   # dfs
+case "$1" in
+  -mkdir) mkdir -p "$(map "$3")" ;;
+  -put) shift; shift; args=("$@"); dst="$(map "${args[-1]}")"; unset 'args[-1]'; mkdir -p "$dst"; cp -r "${args[@]}" "$dst"/ ;;
+  -get) src="$(map "${2%%/\\*}")"; cp -r "$src"/* "$3"/ ;;
+  -test) test -e "$(map "$3")" ;;
+  *) exit 2 ;;
+esac
+""" % root)
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("HADOOP_BIN", str(fake))
+    v = embed.Variable(shape=(100, 4), name="v", num_shards=1)
+    ctx = get_context()
+    ids = torch.arange(10)
+    v.push_gradients(ids, torch.ones(10, 4))
+    v.update_weights()
+    before = v.sparse_read(ids).clone()
+    checkpoint.save_model(ctx, "hdfs://nn/models/m1")
+    assert (root / "models" / "m1" / "model_meta").exists()
+    from openembedding_b200.utils.fs import exists
+    assert exists("hdfs://nn/models/m1") and not exists("hdfs://nn/models/none")
+    v.push_gradients(ids, torch.ones(10, 4))
+    v.update_weights()
+    checkpoint.load_model(ctx, "hdfs://nn/models/m1")
+    assert torch.equal(v.sparse_read(ids), before)
