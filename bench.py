@@ -29,7 +29,7 @@ PUBLISHED_KIPS = {  # BASELINE.md section 1/2, "OpenEmbedding + Horovod" (Cache 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--steps", type=int, default=1000)
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--model", default="deepfm", choices=["lr", "wdl", "deepfm", "xdeepfm", "dcn"])
@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -183,7 +183,6 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
-    clocks = sampler.stop() if rank == 0 else None
     ctx.backend.engine.check()
 
     # ---------------- end-to-end through the public pipeline API: pinned H2D in, loss D2H out, every step
@@ -206,6 +205,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0])
+    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-timed + end-to-end)
     ctx.backend.engine.check()
 
     if rank == 0:
