@@ -5,11 +5,10 @@
 // latency-bound (8 rows in flight per lane group, 25 % occupancy, 8 % of DRAM bandwidth).
 // Two async mechanisms were tried:
 //   * 1-D TMA, one cp.async.bulk (UBLKCP) per row: correct, but the per-SM TMA unit
-//     retires one small copy every ~50-60 cycles -> ~12 us per 384-copy pass; kept only as
-//     helpers (bulk_g2s / bulk_s2g) for large contiguous moves;
+//     retires one small copy every ~50-60 cycles -> ~12 us per 384-copy pass (removed);
 //   * cp.async 16-byte (LDGSTS): a warp instruction moves 512 B in ~8 issue cycles, holds
 //     no registers while in flight and queues arbitrarily deep -> the path used below.
-// A warp keeps a whole pass (32 weight rows, or 16 x {weights, state, accumulator}) in
+// A warp keeps a whole task (32 weight rows, or up to 13 x {weights, state, accumulator}) in
 // flight; peer-mapped (NVLink) addresses take the same path.
 #pragma once
 #include "exb_common.cuh"
@@ -20,47 +19,6 @@ namespace exb {
 #define EXB_APPLY_WARP_BUF 10240  // bytes per warp in the apply phase (w | state | acc rows)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded wait: a lost copy becomes an error code instead of a hung GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity, int* status) {
-    if (mbar_try_wait(b, parity)) return;
-    unsigned long long t0 = globaltimer_ns();
-    unsigned it = 0;
-    while (!mbar_try_wait(b, parity)) {
-        if ((++it & 63u) == 0 && globaltimer_ns() - t0 > EXB_SPIN_TIMEOUT_NS) {
-            set_error(status, EXB_ERR_TIMEOUT_GRID);
-            break;
-        }
-    }
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __noinline__ float4 init_block_masked(const InitParams* I, unsigned long long id, int c, int dim);
 
@@ -76,9 +34,7 @@ __device__ __forceinline__ void cp_async_commit_wait() {
 // Lane l holds (src, id, flag) of row l. buf: EXB_PULL_WARP_BUF bytes owned by this warp.
 __device__ __forceinline__ void pull_rows_bulk(const TableDev& T, const float* src, unsigned long long id,
                                                int flag, int b0, int n_rows, float* __restrict__ out,
-                                               int io_stride, int off, int lane, unsigned char* buf,
-                                               unsigned long long* mbar, unsigned& parity, int* status) {
-    (void)mbar; (void)parity; (void)status;
+                                               int io_stride, int off, int lane, unsigned char* buf) {
     const int wstride = T.wstride;
     const unsigned rowbytes = (unsigned)wstride * 4u;
     const int R = min(32, (int)(EXB_PULL_WARP_BUF / rowbytes));   // rows per pass (warp uniform)

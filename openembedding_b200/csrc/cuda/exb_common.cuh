@@ -39,7 +39,7 @@ struct PlanDev {
     int num_tasks;          // sum_f ceil(B/32)
     int io_stride;          // floats per row of out / grad
     int ncols;              // id columns per batch row (several features may share one column)
-    int use_bulk;           // 1: rows move through shared memory with cp.async.bulk (UBLKCP)
+    int use_bulk;           // 1: rows move through per-warp shared-memory buffers with cp.async (bulk_rows.cuh)
     int _pad1;
     const int* feat_pt;     // [F] feature -> plan-table
     const int* feat_off;    // [F] column offset of the feature in out / grad rows

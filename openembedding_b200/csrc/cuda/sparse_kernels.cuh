@@ -56,12 +56,11 @@ __host__ __device__ inline size_t exb_smem_bytes(int PT, int F, bool push) {
     return (b + 127) & ~(size_t)127;
 }
 // total dynamic shared memory of a 256-thread CTA: staged descriptors | per-warp row buffers |
-// (push: per-warp metadata) | per-warp mbarriers
+// (push: per-warp metadata)
 __host__ __device__ inline size_t exb_smem_total(int PT, int F, bool push) {
     size_t b = exb_smem_bytes(PT, F, push);
     b += 8 * (size_t)(push ? EXB_APPLY_WARP_BUF : EXB_PULL_WARP_BUF);
     if (push) b += 8 * sizeof(WarpMeta);
-    b += 8 * 8;
     return b;
 }
 
@@ -195,12 +194,6 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
     const int wic = threadIdx.x >> 5;
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, false);
     unsigned char* wbuf = stage_end + (size_t)wic * EXB_PULL_WARP_BUF;
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(stage_end + 8 * (size_t)EXB_PULL_WARP_BUF) + wic;
-    unsigned parity = 0;
-    if (P.use_bulk) {
-        if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-        __syncwarp();
-    }
     for (int task = warp; task < P.num_tasks; task += nwarps) {
         const int f = find_segment(S.task_prefix, P.F, task);
         const int b0 = (task - S.task_prefix[f]) * 32;
@@ -237,7 +230,7 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
         }
         const int off = S.feat_off[f];
         if (P.use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
-            pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf, mbar, parity, P.status);
+            pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf);
             continue;
         }
         switch (T.lpr) {
@@ -558,13 +551,6 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, true);
     unsigned char* wbuf = stage_end + (size_t)wic * EXB_APPLY_WARP_BUF;
     WarpMeta* wmeta = reinterpret_cast<WarpMeta*>(stage_end + 8 * (size_t)EXB_APPLY_WARP_BUF) + wic;
-    unsigned long long* mbar =
-        reinterpret_cast<unsigned long long*>(stage_end + 8 * (size_t)EXB_APPLY_WARP_BUF + 8 * sizeof(WarpMeta)) + wic;
-    unsigned parity = 0;
-    if (P.use_bulk) {
-        if ((threadIdx.x & 31) == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-        __syncwarp();
-    }
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
