@@ -183,3 +183,39 @@ esac
     v.update_weights()
     checkpoint.load_model(ctx, "hdfs://nn/models/m1")
     assert torch.equal(v.sparse_read(ids), before)
+
+
+def test_hashing_partitioner():
+    from openembedding_b200.utils.hashing import Partitioner, jump_consistent_hash, murmur3_32, murmur3_fmix64
+    assert murmur3_32(b"") == 0 and murmur3_32(b"", 1) == 0x514E28B7 and murmur3_32(b"hello") == 0x248BFA47
+    assert murmur3_fmix64(0) == 0 and len({murmur3_fmix64(i) for i in range(1000)}) == 1000
+    keys = list(range(20000))
+    a = [jump_consistent_hash(murmur3_fmix64(k), 8) for k in keys]
+    b = [jump_consistent_hash(murmur3_fmix64(k), 9) for k in keys]
+    assert set(a) == set(range(8)) and max(a.count(i) for i in range(8)) < 20000 / 8 * 1.1
+    moved = sum(1 for x, y in zip(a, b) if x != y)
+    assert all(y == 8 for x, y in zip(a, b) if x != y) and 0.08 < moved / 20000 < 0.14    # ~1/9 of the keys move
+    p = Partitioner(5)
+    assert p("model-a") == p(b"model-a") and 0 <= p(12345) < 5
+
+
+def test_native_model_in_process(cpu_context):
+    """NativePS counterpart: load an exported model into this process and pull without any server"""
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    from openembedding_b200.serving.native import NativeModel
+    v = embed.Variable(shape=(1000, 6), name="v", num_shards=1,
+                       initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+    ids = torch.arange(0, 300, 3)
+    v.push_gradients(ids, torch.ones(ids.numel(), 6))
+    v.update_weights()
+    probe = torch.tensor([[0, 3, 6], [1, 2, 999]])        # trained and never-trained rows
+    want = v.sparse_read(probe).clone()
+    d = tempfile.mkdtemp()
+    checkpoint.save_model(get_context(), d + "/m", include_optimizer=False)
+    for shards in (1, 3):
+        m = NativeModel(d + "/m", shard_num=shards)
+        got = m.pull(0, probe)
+        assert got.shape == (2, 3, 6) and torch.allclose(got, want)
+        m.close()
