@@ -29,9 +29,9 @@ def main():
     g = torch.Generator().manual_seed(7)       # same stream on all ranks, each takes its slice
     losses = []
     for step in range(40):
-        ids = torch.randint(0, 1000000, (64, 26), generator=g)
+        ids = torch.randint(0, 1000000, (32 * world, 26), generator=g)
         ids[:, 0] = ids[:, 0] % 50              # a hot column: duplicate ids within and across ranks
-        dense = torch.rand(64, 13, generator=g)
+        dense = torch.rand(32 * world, 13, generator=g)
         y = (ids[:, 0] % 2).float()
         sl = slice(rank * 32, (rank + 1) * 32)
         logit = model(ids[sl], dense[sl])
@@ -57,7 +57,7 @@ def main():
     dist.barrier()
     if rank == 0:
         files = sorted(os.listdir(d[0] + "/ck/0"))
-        assert files == ["model_0_0", "model_1_0"], files
+        assert files == ["model_%d_0" % r for r in range(world)], files
         torch.save({"rows": rows, "dir": d[0]}, os.environ.get("EXB_MP_OUT", d[0] + "/out.pt"))
         print("MP_CPU_CHECK_PASSED", losses[0], losses[-1])
     dist.destroy_process_group()

@@ -6,15 +6,17 @@ import subprocess
 import sys
 import tempfile
 
+import pytest
 import torch
 
 
-def test_criteo_lr_world2_gloo_and_reshard(cpu_context):
+@pytest.mark.parametrize("world", [2, 3])
+def test_criteo_lr_world2_gloo_and_reshard(cpu_context, world):
     here = os.path.dirname(os.path.abspath(__file__))
     out = tempfile.mkdtemp() + "/out.pt"
     env = dict(os.environ, EXB_MP_OUT=out, OMP_NUM_THREADS="1")
-    port = 29600 + os.getpid() % 200
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    port = 29600 + os.getpid() % 200 + world
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mp_cpu_check.py")],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "MP_CPU_CHECK_PASSED" in r.stdout, r.stdout[-3000:]
