@@ -607,6 +607,39 @@ def _DistributedModel(T):
         def save_as_original_model(self, filepath, *args, **kwargs):
             return save_as_original_model(self, filepath, *args, **kwargs)
 
+        def fit(self, data, optimizer, loss_fn, epochs=1, callbacks=(), steps_per_epoch=None, verbose=0):
+            """Minimal Keras-style training loop so that scripts written against the reference's
+            ``model.fit(dataset, epochs=, callbacks=[ModelCheckpoint(...)])`` port one to one
+            (examples/criteo_deepctr_network.py:60-70 of the reference). ``data`` yields
+            ``(inputs, labels)``; ``inputs`` may be a tensor, a tuple/list (positional) or a dict
+            (keyword arguments of ``forward``). Returns ``{"loss": [per-epoch mean]}``."""
+            history = {"loss": []}
+            for cb in callbacks:
+                cb.set_model(self)
+            for epoch in range(epochs):
+                tot, n = 0.0, 0
+                for step, (inputs, labels) in enumerate(data):
+                    if steps_per_epoch is not None and step >= steps_per_epoch:
+                        break
+                    if isinstance(inputs, dict):
+                        out = self(**inputs)
+                    elif isinstance(inputs, (tuple, list)):
+                        out = self(*inputs)
+                    else:
+                        out = self(inputs)
+                    loss = loss_fn(out, labels.to(out.device))
+                    optimizer.zero_grad()
+                    loss.backward()
+                    optimizer.step()
+                    tot += float(loss.detach())
+                    n += 1
+                history["loss"].append(tot / max(n, 1))
+                if verbose and get_context().rank == 0:
+                    print("Epoch %d/%d - loss: %.4f" % (epoch + 1, epochs, history["loss"][-1]))
+                for cb in callbacks:
+                    cb.on_epoch_end(epoch, {"loss": history["loss"][-1]})
+            return history
+
     _Model.__name__ = T.__name__
     _Model.__qualname__ = T.__qualname__
     _DistributedModelClass[T] = _Model
@@ -615,6 +648,26 @@ def _DistributedModel(T):
 
 
 Model = _DistributedModel(nn.Module)
+
+
+class ModelCheckpoint:
+    """``ModelCheckpoint(filepath, save_weights_only=True)`` for ``Model.fit``: after every epoch calls
+    ``model.save_weights`` (server tables INCLUDING optimizer state, like the reference's Keras callback
+    path, exb.py:563-567) or ``model.save``; ``{epoch}`` in ``filepath`` is replaced by the 1-based epoch."""
+
+    def __init__(self, filepath, save_weights_only=True, include_optimizer=True):
+        self.filepath, self.save_weights_only, self.include_optimizer = filepath, save_weights_only, include_optimizer
+        self.model = None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_epoch_end(self, epoch, logs=None):
+        path = self.filepath.format(epoch=epoch + 1)
+        if self.save_weights_only:
+            self.model.save_weights(path)
+        else:
+            self.model.save(path, include_optimizer=self.include_optimizer)
 
 
 def distributed_model(model, sparse_as_dense_size=64, num_shards=None, override_method=True, explicit=False):

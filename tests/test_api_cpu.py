@@ -154,3 +154,36 @@ def test_embedding_multi_hot_bags(cpu_context):
     nt = torch.nested.nested_tensor([torch.tensor([1, 2, 3]), torch.tensor([4])])
     res = emb(nt)
     assert res.is_nested and [tuple(t.shape) for t in res.unbind()] == [(3, 4), (1, 4)]
+
+
+def test_fit_with_model_checkpoint(cpu_context):
+    """Keras-style loop: model.fit(data, optimizer, loss, epochs, callbacks=[ModelCheckpoint]) then reload"""
+    import os
+    import tempfile
+    import openembedding_b200.torch as embed
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(200, 4)
+            self.out = torch.nn.Linear(4, 1)
+
+        def forward(self, ids):
+            return self.out(self.emb(ids)).squeeze(-1)
+
+    torch.manual_seed(0)
+    model = embed.distributed_model(Net(), sparse_as_dense_size=0)
+    opt = embed.distributed_optimizer(torch.optim.Adagrad(model.parameters(), lr=0.5))
+    ids = torch.arange(200)
+    y = (ids % 2).float()
+    data = [(ids[i:i + 50], y[i:i + 50]) for i in range(0, 200, 50)]
+    d = tempfile.mkdtemp()
+    hist = model.fit(data, opt, torch.nn.functional.binary_cross_entropy_with_logits, epochs=6,
+                     callbacks=[embed.ModelCheckpoint(d + "/ck{epoch}")])
+    assert len(hist["loss"]) == 6 and hist["loss"][-1] < hist["loss"][0]
+    assert os.path.exists(d + "/ck6") and os.path.exists(d + "/ck6.openembedding/openembedding/model_meta")
+    want = model(ids).detach().clone()
+    model.fit(data, opt, torch.nn.functional.binary_cross_entropy_with_logits, epochs=1)      # move away ...
+    assert not torch.allclose(model(ids).detach(), want)
+    model.load_weights(d + "/ck6")                                                             # ... and come back
+    assert torch.allclose(model(ids).detach(), want, atol=1e-6)
