@@ -178,6 +178,17 @@ class CpuBackend:
                                          s.ctypes.data if (with_state and sd) else None)
             yield idx, w, (s if with_state else np.empty((n, 0), dtype=np_dt))
 
+    def read_rows(self, meta, global_ids):
+        """(weights, states) of the given rows of this rank's shard (host tier write-back)"""
+        ids = np.ascontiguousarray(np.asarray(global_ids, dtype=np.uint64) // np.uint64(meta.shard_num))
+        np_dt = np.float32 if meta.dtype == "float32" else np.float64
+        sd = self.state_dim(meta)
+        w = np.empty((ids.size, meta.dim), dtype=np_dt)
+        s = np.empty((ids.size, max(sd, 1)), dtype=np_dt)
+        if ids.size:
+            self.lib.exb_var_get_weights(meta.handle, ids.ctypes.data, ids.size, w.ctypes.data, s.ctypes.data if sd else None)
+        return w, s[:, :sd]
+
     def load_rows(self, meta, global_ids, weights, states):
         """rows whose owner is this rank are stored, the rest ignored (load re-shards)."""
         ids = np.asarray(global_ids, dtype=np.uint64)
@@ -358,6 +369,16 @@ class CudaBackend:
             local = (blk // meta.shard_num).cpu().numpy().astype(np.uint64)
             yield local, w.cpu().numpy(), (s.cpu().numpy() if (with_state and s is not None)
                                            else np.empty((blk.numel(), 0), dtype=np.float32))
+
+    def read_rows(self, meta, global_ids):
+        """(weights, states) of the given rows of this rank's shard (host tier write-back): device gather + D2H"""
+        self.ensure_allocated([meta])
+        ids = torch.from_numpy(np.ascontiguousarray(np.asarray(global_ids, dtype=np.uint64).astype(np.int64)))
+        sd = self.state_dim(meta)
+        if ids.numel() == 0:
+            return np.empty((0, meta.dim), np.float32), np.empty((0, sd), np.float32)
+        w, s = self.engine.gather_rows(meta.handle, ids, with_state=True)
+        return w.cpu().numpy(), (s.cpu().numpy() if (s is not None and sd) else np.empty((ids.numel(), 0), np.float32))
 
     def load_rows(self, meta, global_ids, weights, states):
         self.ensure_allocated([meta])

@@ -100,7 +100,8 @@ class TieredVariable:
             ids = self._allgather_ids(ids)
         mine = self._owned(ids).numpy().astype(np.uint64)
         with self._lock:
-            miss = np.array([i for i in mine.tolist() if i not in self.resident], dtype=np.uint64)
+            have = np.fromiter(self.resident.keys(), dtype=np.uint64, count=len(self.resident))
+            miss = mine[~np.isin(mine, have)] if have.size else mine
             self.stats["hits"] += int(mine.size - miss.size)
             self.stats["misses"] += int(miss.size)
             if miss.size == 0:
@@ -125,17 +126,12 @@ class TieredVariable:
 
     # ---- write-back / eviction
     def _cached_rows(self, gids):
-        """(weights, states) of resident rows read back from the cache backend"""
-        want = set(int(x) for x in gids)
-        out_i, out_w, out_s = [], [], []
-        for idx, w, s in self.be.iter_local_rows(self.meta, 1 << 16, with_state=True):
-            gid = idx.astype(np.uint64) * np.uint64(self.meta.shard_num) + np.uint64(max(self.be.shard_id(self.meta), 0))
-            m = np.array([int(g) in want for g in gid])
-            if m.any():
-                out_i.append(gid[m]); out_w.append(np.asarray(w)[m]); out_s.append(np.asarray(s)[m])
-        if not out_i:
-            return np.empty(0, np.uint64), np.empty((0, self.dim), self.np_dt), np.empty((0, self.sd), self.np_dt)
-        return np.concatenate(out_i), np.concatenate(out_w), np.concatenate(out_s)
+        """(ids, weights, states) of resident rows read back from the cache backend (direct gather by id)"""
+        ids = np.ascontiguousarray(np.fromiter((int(x) for x in gids), dtype=np.uint64, count=len(gids)))
+        if ids.size == 0:
+            return ids, np.empty((0, self.dim), self.np_dt), np.empty((0, self.sd), self.np_dt)
+        w, s = self.be.read_rows(self.meta, ids)
+        return ids, np.asarray(w), np.asarray(s)
 
     def _writeback_locked(self, gids):
         if len(gids) == 0:
