@@ -112,6 +112,8 @@ def make_batches(torch, vocab, n_dense, batch, pool, skew, seed, device):
 def main():
     a = parse()
     if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:      # launched under torchrun for N > 1: one line, from rank 0
+            return 0
         print(json.dumps({"impl": "reference", "unavailable":
                           "offline install failed: setup.py needs the CMake-generated openembedding_setup + prebuilt "
                           "libcexb_pack.so (~20 third-party C++ libs fetched by URL) and TensorFlow 2.x + Horovod, "
