@@ -108,3 +108,67 @@ def test_serving_replicas_failover_restore(cpu_context, shard_num, replicas):
         except Exception:
             pass
     httpd.shutdown()
+
+
+def test_daemons_end_to_end(cpu_context):
+    """the deployment of the reference's run/*.sh: masterd + 2 server daemons + controller daemon as separate
+    processes, model created over REST, pulled through the client"""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    from openembedding_b200.master import MasterClient
+    from openembedding_b200.serving.client import ServingClient
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    v = embed.Variable(shape=(500, 4), name="v", num_shards=1, initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+    ids = torch.arange(0, 500, 5)
+    v.push_gradients(ids, torch.ones(ids.numel(), 4))
+    v.update_weights()
+    want = v.sparse_read(torch.arange(40)).clone()
+    d = tempfile.mkdtemp()
+    checkpoint.save_model(get_context(), d + "/m", include_optimizer=False)
+    sign = get_context().model_sign()
+    procs = []
+    try:
+        m = subprocess.Popen([sys.executable, "-m", "openembedding_b200.master", "--port", "0"], cwd=root,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        procs.append(m)
+        endpoint = m.stdout.readline().split()[-1]
+        for _ in range(2):
+            procs.append(subprocess.Popen([sys.executable, "-m", "openembedding_b200.serving.node", "--master_endpoint", endpoint],
+                                          cwd=root, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        mc = MasterClient(endpoint)
+        t0 = time.time()
+        while len(mc.tree_node_sub("nodes")) < 2:
+            assert time.time() - t0 < 60, "server daemons did not register"
+            time.sleep(0.1)
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        procs.append(subprocess.Popen([sys.executable, "-m", "openembedding_b200.serving.controller", "--master_endpoint", endpoint,
+                                       "--port", str(port), "--bind_ip", "127.0.0.1"], cwd=root,
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        base = "http://127.0.0.1:%d" % port
+        t0 = time.time()
+        while True:
+            try:
+                urllib.request.urlopen(base + "/nodes", timeout=2).read()
+                break
+            except Exception:
+                assert time.time() - t0 < 60, "controller daemon did not come up"
+                time.sleep(0.2)
+        req = urllib.request.Request(base + "/models", method="POST", headers={"Content-Type": "application/json"},
+                                     data=json.dumps({"model_uri": d + "/m", "replica_num": 2, "shard_num": -1}).encode())
+        assert json.loads(urllib.request.urlopen(req, timeout=120).read())["model_sign"] == sign
+        assert json.loads(urllib.request.urlopen(base + "/models/" + sign).read())["model_status"] == "NORMAL"
+        got = ServingClient(endpoint).find_model_variable(sign, 0).pull(torch.arange(40))
+        assert torch.allclose(got, want)
+    finally:
+        for p in reversed(procs):
+            p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
