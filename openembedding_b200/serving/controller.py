@@ -151,13 +151,25 @@ class ModelController:
     # ---- HA: a fresh node takes over the shards of a dead one (server --restore,
     #      pico-ps service/Service.cpp:237-313 restore_storages)
     def restore_node(self, new_id, new_endpoint):
+        """A fresh node takes the place of ONE dead node: every shard replica the dead node held (in every
+        model) is re-created on the new node, streamed from a live replica when there is one, else re-read
+        from the model uri (reference: CoordinatedRestoreController, one replacement per dead node)."""
         live = self.nodes()
+        models = self.models()
+        dead = None
+        for rec in models.values():
+            for reps in rec["placement"].values():
+                for nid in reps:
+                    if nid not in live and nid != new_id:
+                        dead = nid if dead is None else min(dead, nid)
+        if dead is None:
+            return []
         restored = []
-        for sign, rec in self.models().items():
+        for sign, rec in models.items():
             changed = False
             for s, reps in rec["placement"].items():
                 for i, nid in enumerate(reps):
-                    if nid in live or nid == new_id:
+                    if nid != dead:
                         continue
                     peers = [p for p in reps if p in live and p != new_id]
                     req = {"model_sign": sign, "model_uri": rec["model_uri"], "shards": [int(s)],
@@ -168,9 +180,6 @@ class ModelController:
                     reps[i] = new_id
                     changed = True
                     restored.append((sign, int(s)))
-                    break   # one node replaces one dead node
-                if changed:
-                    break
             if changed:
                 self.master.tree_node_set("models/" + sign, json.dumps(rec))
         return restored

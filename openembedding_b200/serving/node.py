@@ -55,6 +55,7 @@ class ServingNode:
         self.lib = _native.core()
         self.models = {}        # sign -> {"status","error","uri","shard_num","shards":{(vid,shard):_Shard},"variables":[...]}
         self.lock = threading.RLock()
+        self._load_lock = threading.Lock()
         self.bind_ip = bind_ip or "127.0.0.1"
         node = self
 
@@ -171,22 +172,33 @@ class ServingNode:
     def load_model_async(self, req):
         sign = req["model_sign"]
         with self.lock:
-            self.models[sign] = {"status": "LOADING", "error": "", "uri": req.get("model_uri", ""),
-                                 "shard_num": int(req["shard_num"]), "shards": {}, "variables": []}
+            m = self.models.get(sign)
+            if m is None or int(m["shard_num"]) != int(req["shard_num"]):
+                m = self.models[sign] = {"status": "LOADING", "error": "", "uri": req.get("model_uri", ""),
+                                         "shard_num": int(req["shard_num"]), "shards": {}, "variables": [], "pending": 0}
+            # further requests for the same model ADD shards (a restored node takes over several shard replicas,
+            # each streamed from a different peer); the model is NORMAL again when all of them have landed
+            m["status"] = "LOADING"
+            m["pending"] = m.get("pending", 0) + 1
         threading.Thread(target=self._load, args=(req,), daemon=True).start()
 
     def _load(self, req):
         sign = req["model_sign"]
         try:
-            if req.get("peer"):
-                self._load_from_peer(req)
-            else:
-                self._load_from_fs(req)
+            with self._load_lock:        # loads of one node run one at a time
+                if req.get("peer"):
+                    self._load_from_peer(req)
+                else:
+                    self._load_from_fs(req)
             with self.lock:
-                self.models[sign]["status"] = "NORMAL"
+                m = self.models[sign]
+                m["pending"] = max(0, m.get("pending", 1) - 1)
+                if m["pending"] == 0 and m["status"] != "ERROR":
+                    m["status"] = "NORMAL"
         except Exception as e:      # surfaces through GET /models like the reference's model_error
             log.error("load %s failed: %r", sign, e)
             with self.lock:
+                self.models[sign]["pending"] = max(0, self.models[sign].get("pending", 1) - 1)
                 self.models[sign]["status"] = "ERROR"
                 self.models[sign]["error"] = repr(e)
 
@@ -197,7 +209,11 @@ class ServingNode:
             for sid in req["shards"]:
                 shards[(vid, int(sid))] = _Shard(self.lib, v["datatype"], int(v["embedding_dim"]), int(sid), S, vid)
         with self.lock:
-            self.models[sign]["shards"] = shards
+            old = self.models[sign]["shards"]
+            for k, sh in shards.items():
+                if k in old:
+                    old[k].close()
+                old[k] = sh
             self.models[sign]["variables"] = variables
         return shards
 
@@ -311,12 +327,16 @@ def main(argv=None):
     node = ServingNode(master_endpoint=a.master_endpoint, bind_ip=a.rpc_bind_ip, config=cfg, port=a.port)
     if a.enable_metrics:
         metrics.start_exposer(a.metrics_ip, a.metrics_port)
+    log.info("serving node %d listening on %s", node.node_id, node.endpoint)
+    serving = threading.Thread(target=node.serve_forever, daemon=True)
+    serving.start()                      # the restore below POSTs the shard loads to this very node
     if a.restore and a.master_endpoint:
         from .controller import ModelController
-        ModelController(a.master_endpoint).restore_node(node.node_id, node.endpoint)
-    log.info("serving node %d listening on %s", node.node_id, node.endpoint)
+        restored = ModelController(a.master_endpoint).restore_node(node.node_id, node.endpoint)
+        log.info("restored %d shard replica(s) of a dead node", len(restored))
     try:
-        node.serve_forever()
+        while serving.is_alive():
+            serving.join(1.0)
     except KeyboardInterrupt:
         node.shutdown()
 

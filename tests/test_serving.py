@@ -172,3 +172,79 @@ def test_daemons_end_to_end(cpu_context):
                 p.wait(timeout=10)
             except Exception:
                 p.kill()
+
+
+def test_daemon_sigkill_failover_and_restore(cpu_context):
+    """reference c_api_ha_test: SIGKILL a server process while a client pulls; pulls keep succeeding from the
+    replica; a replacement daemon started with --restore takes over ALL shard replicas of the dead node"""
+    import os
+    import signal
+    import subprocess
+    import sys
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context
+    from openembedding_b200.master import MasterClient
+    from openembedding_b200.serving.client import ServingClient
+    from openembedding_b200.serving.controller import ModelController
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    v = embed.Variable(shape=(600, 4), name="v", num_shards=1, initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+    ids = torch.arange(0, 600, 2)
+    v.push_gradients(ids, torch.ones(ids.numel(), 4))
+    v.update_weights()
+    probe = torch.arange(60)
+    want = v.sparse_read(probe).clone()
+    d = tempfile.mkdtemp()
+    checkpoint.save_model(get_context(), d + "/m", include_optimizer=False)
+    procs = []
+
+    def node(*extra):
+        p = subprocess.Popen([sys.executable, "-m", "openembedding_b200.serving.node", "--master_endpoint", endpoint] + list(extra),
+                             cwd=root, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        procs.append(p)
+        return p
+
+    def wait_nodes(n):
+        t0 = time.time()
+        while len(mc.tree_node_sub("nodes")) != n:
+            assert time.time() - t0 < 60, "expected %d live nodes, have %s" % (n, mc.tree_node_sub("nodes"))
+            time.sleep(0.1)
+    try:
+        m = subprocess.Popen([sys.executable, "-m", "openembedding_b200.master", "--port", "0"], cwd=root,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        procs.append(m)
+        endpoint = m.stdout.readline().split()[-1]
+        mc = MasterClient(endpoint)
+        victims = [node() for _ in range(3)]
+        wait_nodes(3)
+        ctl = ModelController(endpoint)
+        sign = ctl.create_model(d + "/m", replica_num=2, shard_num=3)
+        cli = ServingClient(endpoint)
+        var = cli.find_model_variable(sign, 0)
+        assert torch.allclose(var.pull(probe), want)
+        victims[0].send_signal(signal.SIGKILL)                 # no clean shutdown: the lease has to expire
+        victims[0].wait(timeout=10)
+        for _ in range(5):                                     # pulls fail over to the surviving replicas
+            assert torch.allclose(var.pull(probe, timeout=30), want)
+        wait_nodes(2)
+        node("--restore")
+        wait_nodes(3)
+        t0 = time.time()
+        while True:
+            rec = ctl.show_model(sign)
+            live = set(ctl.nodes())
+            if all(set(reps) <= live for reps in rec["placement"].values()):
+                break
+            assert time.time() - t0 < 60, rec["placement"]
+            time.sleep(0.2)
+        assert all(len(set(reps)) == 2 for reps in rec["placement"].values())
+        assert torch.allclose(ServingClient(endpoint).find_model_variable(sign, 0).pull(probe), want)
+    finally:
+        for p in reversed(procs):
+            if p.poll() is None:
+                p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
