@@ -164,7 +164,11 @@ class TieredVariable:
 
     # ---- bookkeeping called by the variable wrapper
     def mark_updated(self, ids):
-        ids = self._owned(torch.unique(ids.reshape(-1).to("cpu", torch.int64))).tolist()
+        """collective when world > 1: a row this rank owns is dirtied by ANY rank's push"""
+        ids = torch.unique(ids.reshape(-1).to("cpu", torch.int64))
+        if self.ctx.world > 1:
+            ids = self._allgather_ids(ids)
+        ids = self._owned(ids).tolist()
         with self._lock:
             for i in ids:
                 if i in self.resident:

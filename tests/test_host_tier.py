@@ -60,3 +60,17 @@ def test_persist_restore_roundtrip(cpu_context):
     b = _train(emb, opt, 3, seed=4, vocab_hi=200)
     assert a == b
     assert isinstance(embed.should_persist_server_model(None), bool)
+
+
+def test_tier_multi_rank_gloo():
+    """world=2 over gloo: tiered == untiered, rank-local promotion / eviction / write-back"""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29700 + os.getpid() % 200
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mp_cpu_tier_check.py")],
+                       env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "MP_CPU_TIER_CHECK_PASSED" in r.stdout, r.stdout[-3000:]
