@@ -26,3 +26,14 @@ def test_criteo_lr_world2_gloo_and_reshard(cpu_context, world):
     model = CriteoLR(num_sparse=26, num_dense=13, input_dim=1000000, num_shards=16)
     embed.load_server_model(model, saved["dir"] + "/ck")        # world=1 reads the world=2 checkpoint
     assert torch.equal(model.embeddings(torch.arange(0, 50)).detach(), saved["rows"])
+
+
+def test_model_api_world2_gloo():
+    """distributed_model save / load_weights / save_as_original_model on a 2-rank gloo job"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29800 + os.getpid() % 150
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mp_cpu_api_check.py")],
+                       env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "MP_CPU_API_CHECK_PASSED" in r.stdout, r.stdout[-3000:]
