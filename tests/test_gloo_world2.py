@@ -37,3 +37,14 @@ def test_model_api_world2_gloo():
                        env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=300)
     assert r.returncode == 0 and "MP_CPU_API_CHECK_PASSED" in r.stdout, r.stdout[-3000:]
+
+
+def test_fewer_shards_than_ranks_world2_gloo():
+    """num_shards=1 tables (array + hash) on a 2-rank job: round-robin placement, pulls agree, save/load"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29950 + os.getpid() % 40
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "mp_cpu_shards_check.py")],
+                       env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "SHARD1_OK" in r.stdout, r.stdout[-3000:]
