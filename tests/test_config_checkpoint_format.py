@@ -149,3 +149,44 @@ def test_load_reshards_foreign_shard_count(cpu_context):
     open(d + "/model_meta", "w").write(json.dumps(bad))
     with pytest.raises(ValueError):
         embed.load_server_model(None, d)
+
+
+def test_checkpoint_multiple_dump_files_and_optimizer_change(cpu_context):
+    """server.server_dump_files > 1 spreads the shards over files (shard_id % files); loading with a different
+    optimizer category keeps the weights and resets the state (EmbeddingVariable.cpp:44-47)"""
+    import os
+    import tempfile
+    import openembedding_b200 as oe
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import checkpoint
+    from openembedding_b200.context import get_context, reset_context
+    reset_context()
+    old = oe.flags.config
+    oe.flags.config = '{"server": {"server_dump_files": 3}}'
+    try:
+        ctx = get_context()
+        emb = embed.Embedding(1000, 4, embeddings_initializer={"category": "uniform", "minval": -1.0, "maxval": 1.0})
+        opt = embed.distributed_optimizer(torch.optim.Adagrad(emb.parameters(), lr=0.1, initial_accumulator_value=0.1))
+        ids = torch.arange(0, 1000, 3)
+        for _ in range(3):
+            loss = (emb(ids) ** 2).sum()
+            opt.zero_grad(); loss.backward(); opt.step()
+        want = emb(torch.arange(1000)).detach().clone()
+        d = tempfile.mkdtemp()
+        checkpoint.save_model(ctx, d + "/ck", include_optimizer=True)
+        files = sorted(os.listdir(d + "/ck/0"))
+        assert files and all(f.startswith("model_0_") for f in files) and len(files) <= 3
+        # reload into a fresh job that uses a different optimizer: weights survive, state starts over
+        reset_context()
+        ctx = get_context()
+        emb2 = embed.Embedding(1000, 4, embeddings_initializer={"category": "constant", "value": 0.0})
+        opt2 = embed.distributed_optimizer(torch.optim.Adam(emb2.parameters(), lr=0.01))
+        checkpoint.load_model(ctx, d + "/ck")
+        assert torch.equal(emb2(torch.arange(1000)).detach(), want)
+        loss = (emb2(ids) ** 2).sum()
+        opt2.zero_grad(); loss.backward(); opt2.step()          # Adam step from zero moments: |dw| == lr
+        moved = (emb2(ids).detach() - want[ids]).abs()
+        assert torch.allclose(moved[want[ids].abs() > 1e-3], torch.tensor(0.01), atol=2e-4)
+    finally:
+        oe.flags.config = old
+        reset_context()
