@@ -48,3 +48,19 @@ def test_preprocess_tool():
     assert len(lines) == 41 and lines[0].startswith("label,I1") and len(lines[1].split(",")) == 40
     meta = dict(l.split() for l in open(d + "/meta"))
     assert int(meta["C1"]) == 10          # 5 distinct values x 2 repeats
+
+
+def test_deepctr_world2_checkpoint_then_load_in_one_process():
+    """horovodrun -np 2 ... --checkpoint, then load with a different worker count (reference build.sh:136-144)"""
+    d = tempfile.mkdtemp()
+    e = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    port = 29990 - os.getpid() % 30
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), "criteo_deepctr_network.py", "--model", "WDL", "--cpu",
+                        "--epochs", "2", "--batch_size", "16", "--cache", "--checkpoint", d + "/ck"],
+                       cwd=os.path.join(ROOT, "examples"), env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "epoch 2" in r.stdout, r.stdout[-3000:]
+    assert os.path.exists(d + "/ck2/model_meta")
+    out = _run(["criteo_deepctr_network.py", "--model", "WDL", "--cpu", "--epochs", "1", "--batch_size", "16", "--cache",
+                "--load", d + "/ck2"])
+    assert "epoch 1" in out
