@@ -187,3 +187,38 @@ def test_fit_with_model_checkpoint(cpu_context):
     assert not torch.allclose(model(ids).detach(), want)
     model.load_weights(d + "/ck6")                                                             # ... and come back
     assert torch.allclose(model(ids).detach(), want, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,kw,tol", [
+    ("SGD", dict(lr=0.1), 1e-6),
+    ("SGD", dict(lr=0.1, momentum=0.9), 1e-5),
+    ("SGD", dict(lr=0.1, momentum=0.9, nesterov=True), 1e-5),
+    ("Adagrad", dict(lr=0.1, initial_accumulator_value=0.1, eps=1e-7), 1e-5),
+    ("Adam", dict(lr=0.01, betas=(0.9, 0.999), eps=1e-7), 2e-3),
+    ("Adamax", dict(lr=0.01, betas=(0.9, 0.999), eps=1e-7), 2e-3),
+    ("RMSprop", dict(lr=0.01, alpha=0.9, eps=1e-7), 2e-3),
+    ("Adadelta", dict(lr=1.0, rho=0.95, eps=1e-6), 2e-3),
+])
+def test_distributed_optimizer_matches_torch_dense(cpu_context, name, kw, tol):
+    """hyper-parameter translation torch.optim.X -> server optimizer: a server Embedding trained through
+    distributed_optimizer follows a dense nn.Embedding trained with the same torch optimizer (rows touched every step)"""
+    import openembedding_b200.torch as embed
+    torch.manual_seed(0)
+    w0 = torch.randn(20, 5) * 0.1
+    dense = torch.nn.Embedding(20, 5)
+    dense.weight.data.copy_(w0)
+    opt_d = getattr(torch.optim, name)(dense.parameters(), **kw)
+    emb = embed.Embedding(20, 5, embeddings_initializer={"category": "constant", "value": 0.0})
+    ids = torch.arange(20)
+    emb.variable.variable  # created
+    from openembedding_b200.context import get_context
+    get_context().backend.load_rows(emb.variable.variable, ids.numpy().astype("uint64"), w0.numpy(),
+                                    __import__("numpy").empty((20, 0), "float32"))
+    opt_s = embed.distributed_optimizer(getattr(torch.optim, name)(emb.parameters(), **kw))
+    target = torch.randn(20, 5)
+    for _ in range(5):
+        for m, o in ((dense, opt_d), (emb, opt_s)):
+            loss = ((m(ids) - target) ** 2).sum()
+            o.zero_grad(); loss.backward(); o.step()
+    err = (emb(ids).detach() - dense.weight.detach()).abs().max().item()
+    assert err < tol, (name, kw, err)
