@@ -4,6 +4,7 @@ failure -> failover + restore. Reference analogues: c_api_test `model_mix`/`mode
 import json
 import tempfile
 import time
+import urllib.error
 import urllib.request
 
 import pytest
@@ -164,6 +165,22 @@ def test_daemons_end_to_end(cpu_context):
         assert json.loads(urllib.request.urlopen(base + "/models/" + sign).read())["model_status"] == "NORMAL"
         got = ServingClient(endpoint).find_model_variable(sign, 0).pull(torch.arange(40))
         assert torch.allclose(got, want)
+        # REST introspection and teardown (controller.cc: GET/DELETE /models[/sign], GET/DELETE /nodes[/id])
+        assert sign in json.loads(urllib.request.urlopen(base + "/models").read())
+        nodes = json.loads(urllib.request.urlopen(base + "/nodes").read())
+        assert len(nodes) == 2
+        nid = sorted(nodes)[0]
+        assert json.loads(urllib.request.urlopen(base + "/nodes/" + nid).read())["node_id"] == int(nid)
+        req = urllib.request.Request(base + "/models/" + sign, method="DELETE")
+        assert json.loads(urllib.request.urlopen(req).read())["deleted"]
+        with pytest.raises(urllib.error.HTTPError):
+            urllib.request.urlopen(base + "/models/" + sign)
+        req = urllib.request.Request(base + "/nodes/" + nid, method="DELETE")
+        assert json.loads(urllib.request.urlopen(req).read())["shutdown"]
+        t0 = time.time()
+        while len(json.loads(urllib.request.urlopen(base + "/nodes").read())) != 1:
+            assert time.time() - t0 < 30
+            time.sleep(0.2)
     finally:
         for p in reversed(procs):
             p.terminate()
