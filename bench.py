@@ -31,7 +31,10 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=1000)
     p.add_argument("--warmup", type=int, default=20)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "baseline"],
+                   help="ours: this framework; reference: the unmodified reference (unavailable offline); baseline: the same "
+                        "model/config/data in plain PyTorch -- NCCL all_to_all + all_reduce, cuBLAS (benchmarks/nccl_baseline.py)")
+    p.add_argument("--baseline-dtype", default="bf16", choices=["bf16", "fp32"], help="dense compute dtype of --impl baseline")
     p.add_argument("--model", default="deepfm", choices=["lr", "wdl", "deepfm", "xdeepfm", "dcn"])
     p.add_argument("--dim", type=int, default=64)
     p.add_argument("--batch", type=int, default=4096, help="per-GPU batch (weak scaling)")
@@ -109,6 +112,87 @@ def make_batches(torch, vocab, n_dense, batch, pool, skew, seed, device):
     return out
 
 
+def run_baseline(a, torch, dist, world, rank, local_rank):
+    """--impl baseline: plain PyTorch (NCCL + cuBLAS) arm, same metric / config / data / timing rules."""
+    from benchmarks.nccl_baseline import HostPipeline, NcclBaselineCTR
+    from openembedding_b200.models.ctr import CRITEO_1TB_VOCAB_20M, CRITEO_KAGGLE_VOCAB   # constants only
+    vocab = {"criteo1tb_20m": CRITEO_1TB_VOCAB_20M, "kaggle": CRITEO_KAGGLE_VOCAB,
+             "tiny": [min(v, 10007) for v in CRITEO_KAGGLE_VOCAB]}[a.vocab]
+    dev = torch.device("cuda", local_rank)
+    assert a.model in ("deepfm", "wdl") and a.optimizer == "adagrad", "the baseline arm covers DeepFM / WDL with Adagrad"
+    cdt = torch.bfloat16 if a.baseline_dtype == "bf16" else torch.float32
+    model = NcclBaselineCTR(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
+                            cache_threshold=a.cache, compute_dtype=cdt, rank=rank, world=world, device=dev)
+    host = make_batches(torch, vocab, 13, a.batch, a.pool, a.skew, 1000 + rank, dev)
+    devb = [(i.to(dev), d.to(dev), l.to(dev)) for i, d, l in host]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for s in range(a.warmup):
+        model.step(*devb[s % a.pool])
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for s in range(a.steps):
+        loss = model.step(*devb[(a.warmup + s) % a.pool])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    loss_val = float(loss)
+    pipe = HostPipeline(model, a.batch, len(vocab), 13)
+    for s in range(max(3, a.warmup // 2)):
+        pipe.submit(*host[s % a.pool])
+    pipe.last_loss()
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(a.steps):
+        pipe.submit(*host[(a.warmup + s) % a.pool])
+    e2e_loss = pipe.last_loss()
+    f1.record()
+    sync_all()
+    t = torch.tensor([ms, f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        gb = a.batch * world
+        pub = PUBLISHED_KIPS.get((a.model, a.dim), {}).get(world)
+        value = gb * a.steps / (ms / 1e3)
+        rows = sum(vocab)
+        print(json.dumps({
+            "impl": "baseline",
+            "metric": "samples/sec (whole job, device-timed, max over ranks) %s Criteo dim %d" % (a.model, a.dim),
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / (pub * 1e3)) if pub else None, "dtype": a.baseline_dtype,
+            "data": "synthetic (Criteo-shaped: 26 sparse log-uniform ids + 13 dense, random-init weights)",
+            "config": {"model": "%s (DeepCTR architecture), emb dim %d, adagrad sparse / Adagrad dense" % (a.model, a.dim),
+                       "global_batch": gb, "seq_len": 1,
+                       "parallelism": "dp%d + row-sharded embeddings (id %% %d): NCCL all_to_all ids/rows/grads + NCCL all_reduce" % (world, world),
+                       "vocab_rows_total": rows, "cache_threshold": a.cache, "cuda_graph": False,
+                       "engine": "plain PyTorch: torch.unique + index ops, torch.nn / cuBLAS (%s), torch.distributed NCCL" % a.baseline_dtype,
+                       "l2_policy": "inputs larger than L2: %d distinct random batches" % a.pool},
+            "clocks": clocks,
+            "e2e": {"value": gb * a.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                    "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": 0, "nccl_calls_per_step": model.nccl_calls / max(1, a.warmup + 2 * a.steps + max(3, a.warmup // 2)),
+            "final_loss": loss_val, "e2e_final_loss": e2e_loss}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -132,6 +216,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
+    if a.impl == "baseline":
+        return run_baseline(a, torch, dist, world, rank, local_rank)
     import openembedding_b200 as oe
     from openembedding_b200 import _native
     from openembedding_b200.context import get_context

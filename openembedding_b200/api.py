@@ -547,14 +547,20 @@ def save_as_original_model(model, filepath, overwrite=True, include_optimizer=Fa
     engine to serve -- counterpart of exb.py:506-547."""
     if include_optimizer is True:
         raise ValueError("not support include optimizer")
+    ctx = get_context()
     if os.path.exists(filepath) and not overwrite:
         raise IOError("exists: " + filepath)
+    # COLLECTIVE (unlike the reference, whose server processes answer a single caller): the export pulls every
+    # row through the sharded engine, which every rank has to take part in. All ranks run the pulls, only
+    # rank 0 writes the file, and a barrier makes the file visible before anybody returns.
     clone = _to_original(model)
     if type(clone).__name__ in _DistributedModelNames:
         clone.__class__ = clone._Class_base
-    d = os.path.dirname(os.path.abspath(filepath))
-    os.makedirs(d, exist_ok=True)
-    torch.save(clone.cpu(), filepath)
+    if ctx.rank == 0:
+        d = os.path.dirname(os.path.abspath(filepath))
+        os.makedirs(d, exist_ok=True)
+        torch.save(clone.cpu(), filepath)
+    ctx.barrier()
     return clone
 
 

@@ -301,6 +301,15 @@ class CudaBackend:
         self.engine.connect(self.group)
 
     def _plan_for(self, meta, n):
+        """Per-variable plan of capacity next_pow2(n). Creating a plan is collective (IPC exchange) and the
+        push kernel contains cross-GPU barriers, so every rank must pick the SAME plan: with world > 1 the
+        capacity is agreed on first (MAX of n over the ranks) -- uneven last batches / ragged features would
+        otherwise send ranks into different collectives."""
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([int(n)], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n = int(t[0])
         cap = 1024
         while cap < n:
             cap *= 2
@@ -325,12 +334,19 @@ class CudaBackend:
         self._pending.setdefault(meta.variable_id, []).append((ids, grads))
 
     def update(self, metas=None):
+        """Apply the pushed gradients. Collective when world > 1: the kernel is launched on EVERY rank for every
+        variable some rank may have pushed to (n = 0 where this rank has nothing) -- a rank that skipped the
+        launch would leave its peers waiting in the in-kernel barrier."""
         for meta in (metas or self.vars):
             pend = self._pending.pop(meta.variable_id, None)
             if not pend:
-                continue
-            ids = torch.cat([p[0] for p in pend]) if len(pend) > 1 else pend[0][0]
-            g = torch.cat([p[1] for p in pend]) if len(pend) > 1 else pend[0][1]
+                if self.world == 1:
+                    continue
+                ids = torch.zeros((0, 1), dtype=torch.int64, device=self.device)
+                g = torch.zeros((0, meta.dim), dtype=torch.float32, device=self.device)
+            else:
+                ids = torch.cat([p[0] for p in pend]) if len(pend) > 1 else pend[0][0]
+                g = torch.cat([p[1] for p in pend]) if len(pend) > 1 else pend[0][1]
             plan = self._plan_for(meta, ids.shape[0])
             if g.shape[1] != plan.io_stride:
                 gp = torch.zeros((g.shape[0], plan.io_stride), dtype=torch.float32, device=self.device)
@@ -401,20 +417,26 @@ class CudaBackend:
     def table_kind(self, meta):
         return "hash" if meta.is_hash else "array"
 
-    grow_interval, max_load, _steps = 64, 0.5, 0
+    grow_interval, max_load, _steps = 16, 0.5, 0
 
     def tick(self, n=1):
-        """per training step. The reference's hash tables grow on insert (EasyHashMap rehash at load 1/2);
-        here a full shard is an error code of the update kernel, so every `grow_interval` steps the
-        occupancy is read back and shards above `max_load` are doubled (rehash_kernel) on all ranks."""
+        """Per training step (``Context.step_done``).
+
+        * every step: ``engine.poll()`` -- the device error word (hash shard full, inbox / combine-map
+          overflow, barrier timeout) is read back asynchronously and raised as ``StatusError``; no update is
+          ever dropped silently.
+        * every ``grow_interval`` steps: occupancy of the hash shards is read back and shards that would pass
+          ``max_load`` before the NEXT inspection -- judged from the insert rate seen since the last one -- are
+          rehashed to the capacity that keeps them below it (reference: EasyHashMap grows on insert at load 1/2)."""
         before = self._steps
         self._steps += n
+        self.engine.poll()
         if self.grow_interval > 0 and before // self.grow_interval != self._steps // self.grow_interval:
             if any(m.is_hash and m.allocated for m in self.vars):
                 self.maybe_grow(self.max_load)
 
     def maybe_grow(self, load_factor=0.5):
-        """Collective: grow hash shards whose load exceeds `load_factor` (all ranks agree)."""
+        """Collective: grow hash shards whose (projected) load exceeds `load_factor` (all ranks agree)."""
         import torch.distributed as dist
         grew = False
         for meta in self.vars:
@@ -422,11 +444,19 @@ class CudaBackend:
                 continue
             size = self.engine.table_size(meta.handle)
             cap = self.engine.table_info(meta.handle)["rows"]
-            need = torch.tensor([1 if size > cap * load_factor else 0, cap], dtype=torch.int64, device=self.device)
+            last = getattr(meta, "_last_size", 0)
+            rate = max(0, size - last)            # inserts since the previous inspection
+            meta._last_size = size
+            projected = size + 2 * rate           # two more inspection periods of head room
+            need = torch.tensor([projected, cap], dtype=torch.int64, device=self.device)
             if self.world > 1:
                 dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
-            if int(need[0]):
-                self.engine.rehash(meta.handle, int(need[1]) * 2)
+            projected, cap = int(need[0]), int(need[1])
+            if projected > cap * load_factor:
+                new_cap = cap
+                while projected > new_cap * load_factor:
+                    new_cap *= 2
+                self.engine.rehash(meta.handle, new_cap)
                 grew = True
         if grew:
             self.engine.connect(self.group)

@@ -209,13 +209,18 @@ def dump_variable_config(table, reserve_items, optimizer, initializer, include_o
     ini = normalize_initializer(initializer)
     doc = {"table": table, "reserve_items": int(reserve_items)}
     oc, ic = opt.pop("category"), ini.pop("category")
-    ini.pop("seed", None)
+    seed = ini.pop("seed", None)
     if include_optimizer:
         doc["optimizer"] = oc
     doc["initializer"] = ic
     if include_optimizer:
         doc[oc] = opt
     doc[ic] = ini
+    # B200 addition: pulls never insert, so never-updated rows are regenerated from Philox(seed, variable_id).
+    # The seed therefore has to travel with the checkpoint (the reference loader only warns about unknown keys,
+    # Factory.h:64-75); seed 0 (the default) is left out so that default dumps stay byte-identical.
+    if seed:
+        doc["initializer_seed"] = int(seed)
     if extra:
         doc.update(extra)
     return yaml.safe_dump(doc, sort_keys=False, default_flow_style=False)
@@ -235,6 +240,7 @@ def load_variable_config(text):
         cfg = dict(doc.get(ic) or {})
         cfg["category"] = ic
         out["initializer"] = normalize_initializer(cfg)
+        out["initializer"]["seed"] = int(doc.get("initializer_seed", 0))
     return out
 
 

@@ -13,6 +13,7 @@ import torch
 
 from .. import _native
 from ..config import initializer_params, mix_seed, optimizer_params
+from ..status import ENGINE_STATUS, Status, StatusError
 
 _STATUS_TEXT = {
     0: "ok", 1: "grid barrier timeout", 2: "peer barrier timeout (a rank did not arrive)",
@@ -50,6 +51,12 @@ class CudaEngine:
         self.plans = []
         self._sync_connected = self.world == 1
         self._peer_open = []      # opened IPC pointers (closed at destroy)
+        # asynchronous status read-back (poll()): the error word travels D2H on a side stream into pinned memory
+        self._st_stream = torch.cuda.Stream(device=self.device)
+        self._st_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._st_ev = torch.cuda.Event()
+        self._st_pending = False
+        self._st_dev = None
 
     # ---------------------------------------------------------------- tables
     def add_table(self, dim, vocab, is_hash=False, capacity=0, shard_num=-1, shard_base=0):
@@ -189,11 +196,37 @@ class CudaEngine:
                                "update_unique": int(stats[2]), "last_push_update_us": phases,
                                "probe": [int(stats[i]) for i in range(16, 28)]}
 
+    def _raise(self, code):
+        self.lib.exb_engine_reset_status(self.h)
+        raise StatusError(ENGINE_STATUS.get(code, Status.ERROR),
+                          "sparse engine error %d: %s" % (code, _STATUS_TEXT.get(code, "?")))
+
     def check(self):
+        """Blocking (device sync): raise ``StatusError`` if any kernel since the last check left an error
+        code (hash shard full, inbox / combine-map overflow, barrier timeout)."""
         code, _ = self.status()
         if code != 0:
-            self.lib.exb_engine_reset_status(self.h)
-            raise RuntimeError("sparse engine error %d: %s" % (code, _STATUS_TEXT.get(code, "?")))
+            self._raise(code)
+
+    def poll(self):
+        """Non-blocking status check for the per-step product path: consumes the previous asynchronous
+        read-back of the device error word (raises ``StatusError`` if it was non-zero) and enqueues the next
+        one on a side stream -- an error surfaces at most two polls after the kernel that hit it, without a
+        device synchronisation on the training stream."""
+        if self._st_pending and self._st_ev.query():
+            self._st_pending = False
+            code = int(self._st_host[0])
+            if code != 0:
+                self._raise(code)
+        if not self._st_pending:
+            if self._st_dev is None:
+                from .p2p_allreduce import tensor_from_ptr
+                self._st_dev = tensor_from_ptr(self.lib.exb_engine_sync_ptr(self.h) + 132, 1, self.device,
+                                               dtype=torch.int32)
+            with torch.cuda.stream(self._st_stream):
+                self._st_host.copy_(self._st_dev, non_blocking=True)
+                self._st_ev.record(self._st_stream)
+            self._st_pending = True
 
     # ---------------------------------------------- checkpoint-side row access
     def enumerate_ids(self, t):

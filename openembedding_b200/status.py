@@ -6,7 +6,8 @@ state machine that reacts to it (pico-ps/pico-ps/handler/Handler.cpp: retry on T
 / context-version mismatch after refreshing the context from the master).
 
 Here the training data plane is a set of kernels: a failed verb leaves a device-resident error
-code (``csrc/cuda/exb_common.cuh: ExbStatus``) that ``CudaEngine.check()`` turns into
+code (``csrc/cuda/exb_common.cuh: ExbStatus``) that ``CudaEngine.check()`` (blocking) and
+``CudaEngine.poll()`` (asynchronous read-back, called every step by ``CudaBackend.tick``) turn into
 ``StatusError``; the serving client maps transport failures to NO_REPLICA / TIMEOUT and retries
 (``serving/client.py``). ``SERVER_TOO_*_CTX`` has no counterpart in training (no server processes
 whose table context could lag); in serving the equivalent is a stale placement record, refreshed
