@@ -47,6 +47,9 @@ def parse():
     p.add_argument("--allreduce", default="auto")
     p.add_argument("--skew", type=float, default=1.0, help="0 = uniform ids, 1 = log-uniform (Zipf-like)")
     p.add_argument("--pool", type=int, default=16, help="distinct pre-generated batches cycled through")
+    p.add_argument("--prefetch", action="store_true",
+                   help="announce the next batch's ids one step ahead (plan prefetch on a side stream, the reference's pulling()); "
+                        "measured slower than planning inside the pull launch, hence off by default")
     return p.parse_args()
 
 
@@ -236,6 +239,7 @@ def main():
         model = FusedCTR(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
                          sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
         trainer = FusedTrainer(model, use_graph=not a.no_graph)
+        trainer.want_prefetch = bool(a.prefetch)
     else:
         model = CTRModel(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
                          sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
@@ -250,9 +254,16 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    prefetch = engine == "fused" and a.prefetch
+
+    def run_step(k):
+        if prefetch:      # public prefetch API: the ids of the NEXT batch are announced one step ahead (reference: pulling())
+            return trainer.step(*devb[k % a.pool], next_ids=devb[(k + 1) % a.pool][0])
+        return trainer.step(*devb[k % a.pool])
+
     # ---------------- device-timed headline number
     for s in range(a.warmup):
-        trainer.step(*devb[s % a.pool])
+        run_step(s)
     sync_all()
     ctx.backend.engine.check()
     sampler = ClockSampler(local_rank)
@@ -262,7 +273,7 @@ def main():
     sync_all()
     e0.record()
     for s in range(a.steps):
-        loss = trainer.step(*devb[(a.warmup + s) % a.pool])
+        loss = run_step(a.warmup + s)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -315,7 +326,7 @@ def main():
             "config": {"model": "%s (DeepCTR architecture), emb dim %d, %s sparse / Adagrad dense" % (a.model, a.dim, a.optimizer),
                        "global_batch": gb, "seq_len": 1, "parallelism": "dp%d + row-sharded embeddings (id %% %d) over NVLink" % (world, world),
                        "vocab_rows_total": rows, "tables_fp32_gb": round(rows * (a.dim + 1) * 4 * 2 / 2 ** 30, 1),
-                       "cache_threshold": a.cache, "cuda_graph": not a.no_graph, "engine": engine,
+                       "cache_threshold": a.cache, "cuda_graph": not a.no_graph, "engine": engine, "prefetch": prefetch,
                        "l2_policy": "inputs larger than L2: %d distinct random batches over a %.0f GB table working set" % (
                            a.pool, rows * (a.dim + 1) * 8 / 2 ** 30)},
             "clocks": clocks,
@@ -325,6 +336,9 @@ def main():
             "native_libs": {"cuda": _native.cuda_loaded()},
             "final_loss": loss_val, "e2e_final_loss": e2e_loss,
             "push_update_phases_us": ctx.backend.engine.status()[1].get("last_push_update_us"),
+            "sparse_counters": {k: v for k, v in ctx.backend.engine.status()[1].items()
+                                if k in ("pull_indices", "pull_unique", "push_indices", "update_unique",
+                                         "nvlink_rows_pulled", "nvlink_rows_pushed", "plans")},
         }
         print(json.dumps(line))
     if world > 1:

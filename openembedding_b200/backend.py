@@ -241,7 +241,7 @@ class _CpuGroup:
     def feature_slices(self):
         return [slice(o, o + d) for o, d in zip(self.feat_offsets, self.dims)]
 
-    def pull(self, ids):
+    def pull(self, ids, out=None, train=False):
         out = torch.empty((ids.shape[0], self.io_stride), dtype=torch.float32)
         for f, m in enumerate(self.metas):
             out[:, self.feat_offsets[f]:self.feat_offsets[f] + m.dim] = self.b.pull(m, ids[:, self.feat_cols[f]]).to(torch.float32)

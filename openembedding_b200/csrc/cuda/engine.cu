@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "sparse_kernels.cuh"
+#include "sparse_v2.cuh"
 
 using namespace exb;
 
@@ -55,9 +56,10 @@ struct Plan {
     char* meta = nullptr;   // small index arrays
     char* inbox = nullptr;  // keys | grads | cnt (peer mapped)
     size_t inbox_bytes = 0, inbox_grads_off = 0, inbox_cnt_off = 0;
-    char* work = nullptr;   // send_cnt | ucount | cmap_keys | cmap_cnt | ulist | acc
-    int grid_pull = 1, grid_push = 1;
-    size_t smem_pull = 0, smem_push = 0;
+    char* work = nullptr;   // send_cnt | parity | 2 x (ucount | cmap_keys | cmap_cnt | ulist | ukeys | slot_of | acc | urows)
+    size_t inbox_vals_off = 0, work_bytes = 0;
+    int grid_pull = 1, grid_push = 1, grid_pull2 = 1, grid_plan = 1;
+    size_t smem_pull = 0, smem_push = 0, smem_pull2 = 0, smem_plan = 0;
 };
 
 int pow2_ceil_int(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -672,26 +674,47 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     d.pt_ulist_off = (const unsigned long long*)(p->meta + o_uoff);
     // ---- inbox (peer visible): keys | grads | cnt
     size_t kb = align_up((size_t)W * ko * 8, 256), gb = align_up((size_t)W * go * 4, 256), cb = align_up((size_t)W * PT * 4, 256);
-    if (W == 1) { kb = 256; gb = 256; }
-    p->inbox_grads_off = kb; p->inbox_cnt_off = kb + gb;
-    p->inbox_bytes = align_up(kb + gb + cb, 2u << 20);
+    size_t vb = align_up((size_t)W * ko * 4, 256);
+    if (W == 1) { kb = 256; gb = 256; vb = 256; }
+    p->inbox_grads_off = kb; p->inbox_cnt_off = kb + gb; p->inbox_vals_off = kb + gb + cb;
+    p->inbox_bytes = align_up(kb + gb + cb + vb, 2u << 20);
     CKP(cudaMalloc(&p->inbox, p->inbox_bytes));
     CKP(cudaMemset(p->inbox + p->inbox_cnt_off, 0, cb));
     d.inbox_keys[e->rank] = (unsigned long long*)p->inbox;
     d.inbox_grads[e->rank] = (float*)(p->inbox + p->inbox_grads_off);
     d.inbox_cnt[e->rank] = (unsigned*)(p->inbox + p->inbox_cnt_off);
-    // ---- local work: send_cnt | ucount | cmap_keys | cmap_cnt | ulist | acc
+    d.inbox_vals[e->rank] = (unsigned*)(p->inbox + p->inbox_vals_off);
+    // ---- local work: send_cnt | parity | 2 slots x (ucount | cmap_keys | cmap_cnt | ulist | ukeys | slot_of | acc | urows)
     size_t woff = 0;
     auto wtake = [&](size_t bytes) { size_t o = woff; woff = align_up(woff + bytes, 256); return o; };
-    size_t o_send = wtake((size_t)W * PT * 4 * EXB_CTR_STRIDE), o_ucount = wtake((size_t)PT * 4 * EXB_CTR_STRIDE), o_ckeys = wtake(mo * 8), o_ccnt = wtake(mo * 4),
-           o_ulist = wtake(uo * 4), o_ukeys = wtake(uo * 8), o_acc = wtake(ao * 4);
+    size_t o_send = wtake((size_t)W * PT * 4 * EXB_CTR_STRIDE), o_par = wtake(256);
+    size_t o_ucount[2], o_ckeys[2], o_ccnt[2], o_ulist[2], o_ukeys[2], o_slotof[2], o_acc[2], o_urows[2];
+    size_t o_ocount[2], o_olist[2], o_okeys[2];
+    for (int s = 0; s < 2; ++s) {
+        o_ucount[s] = wtake((size_t)PT * 4 * EXB_CTR_STRIDE); o_ckeys[s] = wtake(mo * 8); o_ccnt[s] = wtake(mo * 4);
+        o_ulist[s] = wtake(uo * 4); o_ukeys[s] = wtake(uo * 8); o_slotof[s] = wtake((size_t)F * B * 4);
+        o_acc[s] = wtake(ao * 4); o_urows[s] = wtake(W > 1 ? ao * 4 : 256);
+        o_ocount[s] = wtake((size_t)PT * 4 * EXB_CTR_STRIDE);
+        o_olist[s] = wtake(W > 1 ? uo * 4 : 256); o_okeys[s] = wtake(W > 1 ? uo * 8 : 256);
+    }
+    p->work_bytes = woff;
     CKP(cudaMalloc(&p->work, woff));
     CKP(cudaMemset(p->work, 0, woff));
-    fill_u64_kernel<<<e->sms * 4, 256>>>((unsigned long long*)(p->work + o_ckeys), mo, EXB_EMPTY_KEY);
-    CKP(cudaGetLastError());
-    d.send_cnt = (unsigned*)(p->work + o_send); d.ucount = (unsigned*)(p->work + o_ucount);
-    d.cmap_keys = (unsigned long long*)(p->work + o_ckeys); d.cmap_cnt = (unsigned*)(p->work + o_ccnt);
-    d.ulist = (unsigned*)(p->work + o_ulist); d.ukeys = (unsigned long long*)(p->work + o_ukeys); d.acc = (float*)(p->work + o_acc);
+    for (int s = 0; s < 2; ++s) {
+        fill_u64_kernel<<<e->sms * 4, 256>>>((unsigned long long*)(p->work + o_ckeys[s]), mo, EXB_EMPTY_KEY);
+        CKP(cudaGetLastError());
+        SlotDev& L = d.slot[s];
+        L.ucount = (unsigned*)(p->work + o_ucount[s]); L.cmap_keys = (unsigned long long*)(p->work + o_ckeys[s]);
+        L.cmap_cnt = (unsigned*)(p->work + o_ccnt[s]); L.ulist = (unsigned*)(p->work + o_ulist[s]);
+        L.ukeys = (unsigned long long*)(p->work + o_ukeys[s]); L.slot_of = (unsigned*)(p->work + o_slotof[s]);
+        L.acc = (float*)(p->work + o_acc[s]); L.urows = (float*)(p->work + o_urows[s]);
+        L.ocount = (unsigned*)(p->work + o_ocount[s]); L.olist = (unsigned*)(p->work + o_olist[s]);
+        L.okeys = (unsigned long long*)(p->work + o_okeys[s]);
+    }
+    d.send_cnt = (unsigned*)(p->work + o_send); d.parity = (unsigned*)(p->work + o_par);
+    // the v1 kernels work on slot 0
+    d.ucount = d.slot[0].ucount; d.cmap_keys = d.slot[0].cmap_keys; d.cmap_cnt = d.slot[0].cmap_cnt;
+    d.ulist = d.slot[0].ulist; d.ukeys = d.slot[0].ukeys; d.acc = d.slot[0].acc;
     // ---- sync words
     for (int r = 0; r < W; ++r) d.flags[r] = (unsigned*)(e->sync_peer[r] + OFF_FLAGS);
     d.gbar = (unsigned*)(e->sync_local + OFF_GBAR);
@@ -720,7 +743,27 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pull, exb_pull_kernel, 256, p->smem_pull);
     if (occ_pull < 1) occ_pull = 1;
     p->grid_pull = std::max(1, std::min(e->sms * occ_pull, (d.num_tasks + 7) / 8));
-    if (e->max_ctas > 0) { p->grid_push = std::min(p->grid_push, e->max_ctas); p->grid_pull = std::min(p->grid_pull, e->max_ctas); }
+    // ---- v2 kernels (sparse_v2.cuh)
+    p->smem_plan = exb_smem_bytes(PT, F, false);
+    p->smem_pull2 = exb_smem_bytes(PT, F, true) + 8 * (size_t)EXB_PULL_WARP_BUF;
+    cudaFuncSetAttribute(exb_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(exb_pull2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(exb_pull_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(exb_push2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    p->grid_plan = std::max(1, (d.num_tasks + 7) / 8);
+    {
+        int occ2 = 1;      // the pull2 kernel contains a grid barrier: all CTAs resident
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, exb_pull2_kernel, 256, p->smem_pull2);
+        occ2 = std::max(1, std::min(occ2, 2));
+        p->grid_pull2 = std::max(1, std::min(e->sms * occ2, (d.num_tasks + 7) / 8));
+        int occ3 = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, exb_push2_kernel, 256, p->smem_push);
+        if (occ3 < per_sm) p->grid_push = std::min(p->grid_push, e->sms * std::max(1, occ3));
+    }
+    if (e->max_ctas > 0) {
+        p->grid_push = std::min(p->grid_push, e->max_ctas); p->grid_pull = std::min(p->grid_pull, e->max_ctas);
+        p->grid_pull2 = std::min(p->grid_pull2, e->max_ctas); p->grid_plan = std::min(p->grid_plan, 4 * e->max_ctas);
+    }
     CKP(cudaDeviceSynchronize());
     return p;
 }
@@ -741,6 +784,7 @@ int exb_plan_set_peer_inbox(void* ph, int peer, uint64_t base) {
     p->d.inbox_keys[peer] = (unsigned long long*)base;
     p->d.inbox_grads[peer] = (float*)((char*)base + p->inbox_grads_off);
     p->d.inbox_cnt[peer] = (unsigned*)((char*)base + p->inbox_cnt_off);
+    p->d.inbox_vals[peer] = (unsigned*)((char*)base + p->inbox_vals_off);
     return 0;
 }
 // refresh flag pointers after peers' sync blocks were imported
@@ -774,5 +818,55 @@ int exb_push_update(void* ph, uint64_t ids, uint64_t grads, int n_rows, uint64_t
                   (const TableDev*)e->d_tables, p->d, (const long long*)ids, (const float*)grads, n_rows));
     return 0;
 }
+
+// ---- v2: plan once per step (sparse_v2.cuh). which: 0 = current slot, 1 = next slot (prefetch)
+int exb_plan_prepare(void* ph, uint64_t ids, int n_rows, int which, uint64_t stream) {
+    Plan* p = (Plan*)ph;
+    Engine* e = p->e;
+    if (n_rows > p->d.B) return fail_msg("prepare: n_rows exceeds plan batch");
+    CK(launch_pdl(exb_plan_kernel, dim3(p->grid_plan), dim3(256), p->smem_plan, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const long long*)ids, n_rows, which));
+    return 0;
+}
+int exb_plan_reset(void* ph, int which, uint64_t stream) {
+    Plan* p = (Plan*)ph;
+    exb_plan_reset_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->d, which);
+    CK(cudaGetLastError());
+    return 0;
+}
+int exb_pull2(void* ph, uint64_t ids, uint64_t out, int n_rows, int which, uint64_t stream) {
+    Plan* p = (Plan*)ph;
+    Engine* e = p->e;
+    if (n_rows > p->d.B) return fail_msg("pull: n_rows exceeds plan batch");
+    CK(launch_pdl(exb_pull2_kernel, dim3(p->grid_pull2), dim3(256), p->smem_pull2, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const long long*)ids, (float*)out, n_rows, which));
+    return 0;
+}
+// training pull: one-pass gather + plan of the batch in the same launch (exb_pull_plan_kernel)
+int exb_pull_plan(void* ph, uint64_t ids, uint64_t out, int n_rows, int which, uint64_t stream) {
+    Plan* p = (Plan*)ph;
+    Engine* e = p->e;
+    if (n_rows > p->d.B) return fail_msg("pull: n_rows exceeds plan batch");
+    int grid = std::max(1, std::min(p->grid_pull * 8 / EXB_PP_GATHER_WARPS + 1, e->sms * 3));
+    if (e->max_ctas > 0) grid = std::min(grid, e->max_ctas);
+    CK(launch_pdl(exb_pull_plan_kernel, dim3(grid), dim3(256), p->smem_pull, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const long long*)ids, (float*)out, n_rows, which));
+    return 0;
+}
+int exb_push2(void* ph, uint64_t grads, int n_rows, int which, uint64_t stream) {
+    Plan* p = (Plan*)ph;
+    Engine* e = p->e;
+    if (n_rows > p->d.B) return fail_msg("push: n_rows exceeds plan batch");
+    CK(launch_pdl(exb_push2_kernel, dim3(p->grid_push), dim3(256), p->smem_push, (cudaStream_t)stream,
+                  (const TableDev*)e->d_tables, p->d, (const float*)grads, n_rows, which));
+    return 0;
+}
+// bytes of device memory held by a plan: out[0] = peer-visible inbox, out[1] = local work area (both slots)
+int exb_plan_memory(void* ph, uint64_t* out) {
+    Plan* p = (Plan*)ph;
+    out[0] = p->inbox_bytes; out[1] = p->work_bytes;
+    return 0;
+}
+uint64_t exb_engine_status_ptr(void* h) { return (uint64_t)(((Engine*)h)->sync_local + OFF_STATUS); }
 
 }  // extern "C"

@@ -34,6 +34,22 @@ struct TableDev {
     OptParams opt;
 };
 
+// One batch slot of a plan (sparse_v2.cuh): the per-step de-duplication state. A plan owns two (double buffer:
+// the plan of batch k+1 is built while batch k trains); slot[0] aliases the v1 work arrays below.
+struct SlotDev {
+    unsigned long long* cmap_keys;   // per-table open-addressing maps id -> h
+    unsigned* cmap_cnt;              // [h] lookups of the id in the batch (+ counts received from peers)
+    float* acc;                      // [h] summed gradient row
+    float* urows;                    // [h] staging row of a remote unique id (pull)
+    unsigned* ulist;                 // unique entries in insertion order: h ...
+    unsigned long long* ukeys;       // ... and id
+    unsigned* ucount;                // [PT * EXB_CTR_STRIDE]
+    unsigned* slot_of;               // [F][B] h of every lookup (0xFFFFFFFF: invalid id)
+    unsigned* olist;                 // world > 1: unique entries OWNED by this rank (own lookups + received), the
+    unsigned long long* okeys;       //            work list of the optimizer phase
+    unsigned* ocount;                // [PT * EXB_CTR_STRIDE]
+};
+
 struct PlanDev {
     int F, B, PT, W, rank;
     int num_tasks;          // sum_f ceil(B/32)
@@ -70,6 +86,9 @@ struct PlanDev {
     int* status;                                    // 0 ok; else first error code
     unsigned long long* stats;                      // [0] pull ids, [1] push ids, [2] unique rows updated
     unsigned long long* trace;                      // optional per-warp %globaltimer trace (EXB_TRACE_SLOTS per warp)
+    SlotDev slot[2];                                // v2 batch slots
+    unsigned* parity;                               // which slot is "current" (flipped by exb_push2_kernel)
+    unsigned* inbox_vals[EXB_MAX_PEERS];            // peer mapped: count of every inbox entry (parallel to inbox_keys)
 };
 #define EXB_TRACE_SLOTS 32
 

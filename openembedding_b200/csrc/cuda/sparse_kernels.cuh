@@ -179,6 +179,59 @@ __device__ __forceinline__ void pull_rows(const TableDev& T, const float* src, u
     }
 }
 
+// one warp task of the pull: the 32 lookups (f, b0 .. b0+31)
+__device__ __forceinline__ void pull_one_task(const SmemView& S, const PlanDev& P, const long long* __restrict__ ids,
+                                              float* __restrict__ out, int n_rows, int task, int lane,
+                                              unsigned char* wbuf) {
+    const int W = P.W;
+    const int f = find_segment(S.task_prefix, P.F, task);
+    const int b0 = (task - S.task_prefix[f]) * 32;
+    if (b0 >= n_rows) return;
+    const TableDev& T = S.tab[S.feat_pt[f]];
+    const int b = b0 + lane;
+    unsigned long long id = 0;
+    const float* src = nullptr;
+    int flag = 0;
+    if (b < n_rows) {
+        id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + S.feat_col[f]);
+        if (!T.is_hash) {
+            if (id < T.vocab) {
+                int o = owner_of(T, id, W);
+                src = T.w[o] + local_row_of(T, id) * (unsigned long long)T.wstride;
+                flag = 1;
+            }
+        } else if ((id >> 63) == 0) {
+            int o = owner_of(T, id, W);
+            const unsigned long long* keys = T.keys[o];
+            unsigned long long mask = T.rows - 1, h = exb_hash64(id) & mask;
+            flag = 2;
+            for (unsigned long long probe = 0; probe <= mask; ++probe) {
+                unsigned long long k = keys[h];
+                if (k == id) {
+                    src = T.w[o] + h * (unsigned long long)T.wstride;
+                    flag = 1;
+                    break;
+                }
+                if (k == EXB_EMPTY_KEY) break;
+                h = (h + 1) & mask;
+            }
+        }
+    }
+    const int off = S.feat_off[f];
+    if (P.use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
+        pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf);
+        return;
+    }
+    switch (T.lpr) {
+        case 1: pull_rows<1>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+        case 2: pull_rows<2>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+        case 4: pull_rows<4>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+        case 8: pull_rows<8>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+        case 16: pull_rows<16>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+        default: pull_rows<32>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
+    }
+}
+
 __global__ void __launch_bounds__(256, 3)
 exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long* __restrict__ ids,
                 float* __restrict__ out, int n_rows) {
@@ -189,59 +242,12 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int W = P.W;
-    if (W > 1) peer_wait(P);   // peers' last update is complete (deferred half of the push "done" barrier)
+    if (P.W > 1) peer_wait(P);   // peers' last update is complete (deferred half of the push "done" barrier)
     const int wic = threadIdx.x >> 5;
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, false);
     unsigned char* wbuf = stage_end + (size_t)wic * EXB_PULL_WARP_BUF;
-    for (int task = warp; task < P.num_tasks; task += nwarps) {
-        const int f = find_segment(S.task_prefix, P.F, task);
-        const int b0 = (task - S.task_prefix[f]) * 32;
-        if (b0 >= n_rows) continue;
-        const TableDev& T = S.tab[S.feat_pt[f]];
-        const int b = b0 + lane;
-        unsigned long long id = 0;
-        const float* src = nullptr;
-        int flag = 0;
-        if (b < n_rows) {
-            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + S.feat_col[f]);
-            if (!T.is_hash) {
-                if (id < T.vocab) {
-                    int o = owner_of(T, id, W);
-                    src = T.w[o] + local_row_of(T, id) * (unsigned long long)T.wstride;
-                    flag = 1;
-                }
-            } else if ((id >> 63) == 0) {
-                int o = owner_of(T, id, W);
-                const unsigned long long* keys = T.keys[o];
-                unsigned long long mask = T.rows - 1, h = exb_hash64(id) & mask;
-                flag = 2;
-                for (unsigned long long probe = 0; probe <= mask; ++probe) {
-                    unsigned long long k = keys[h];
-                    if (k == id) {
-                        src = T.w[o] + h * (unsigned long long)T.wstride;
-                        flag = 1;
-                        break;
-                    }
-                    if (k == EXB_EMPTY_KEY) break;
-                    h = (h + 1) & mask;
-                }
-            }
-        }
-        const int off = S.feat_off[f];
-        if (P.use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
-            pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf);
-            continue;
-        }
-        switch (T.lpr) {
-            case 1: pull_rows<1>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-            case 2: pull_rows<2>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-            case 4: pull_rows<4>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-            case 8: pull_rows<8>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-            case 16: pull_rows<16>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-            default: pull_rows<32>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        }
-    }
+    for (int task = warp; task < P.num_tasks; task += nwarps)
+        pull_one_task(S, P, ids, out, n_rows, task, lane, wbuf);
     if (threadIdx.x == 0 && blockIdx.x == 0)
         atomicAdd(&P.stats[0], (unsigned long long)n_rows * (unsigned long long)P.F);
 }
@@ -559,6 +565,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     // stats[8..15] (read by utils.timers; the in-kernel equivalent of the reference's VTIMER)
 #define EXB_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[8 + (i)] = globaltimer_ns(); } while (0)
     EXB_STAMP(0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.stats[7] = 1ull;     // phase-clock layout marker (v2 kernel writes 2)
 
     // ---------------- P1: dispatch (remote ids -> owner inbox, local ids -> combine map)
     for (int task = warp; task < P.num_tasks; task += nwarps) {

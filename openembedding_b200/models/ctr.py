@@ -40,7 +40,7 @@ class _GroupLookup(torch.autograd.Function):
     def forward(ctx, anchor, ids, owner):
         ctx.owner = owner
         ctx.ids = ids
-        return owner.group.pull(ids)
+        return owner.group.pull(ids, train=True)    # push_update of the same ids follows in backward
 
     @staticmethod
     def backward(ctx, grad):

@@ -214,7 +214,7 @@ class FusedCTR:
         # weight-gradient GEMMs read the batch-major activations as MN-major operands: no A0^T / H^T / dZ^T copies
         self.mn_major = os.environ.get("EXB_MN_MAJOR", "1") != "0"
         self._s2 = torch.cuda.Stream(device=dev)
-        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork, self._ev_join, self._ev_plan = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         assert L <= 4, "the fused optimizer kernel takes at most 4 weight matrices"
         oa = _DenseOptArgs()
         oa.theta, oa.accum, oa.grad = self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr()
@@ -255,14 +255,34 @@ class FusedCTR:
                                           self.WTb[l].data_ptr(), self.Hp[l], dims[l], self._st()), "refresh_bf16")
 
     # ---- one training step (all launches on the current stream)
-    def forward_backward(self, ids, dense, labels, update=True):
+    def forward_backward(self, ids, dense, labels, update=True, next_ids=None, planned=False):
+        """``next_ids``: ids of the NEXT batch (device tensor that stays unchanged until that batch has been
+        trained) -- its de-duplication plan is built on a side stream while this batch computes (prefetch, the
+        reference's ``pulling``). ``planned``: the caller guarantees that the current batch slot already holds the
+        plan of ``ids`` (CUDA-graph replays, where the python bookkeeping of the plan is bypassed)."""
         B, L, lib, st = self.B, len(self.hidden), self.lib, self._st()
         assert ids.shape == (B, self.nf) and ids.dtype == torch.int64 and ids.is_contiguous()
         if self._grad_dirty:          # the optimizer kernel clears the gradients it consumed; a call with
             self.gtheta.zero_()       # update=False leaves them behind
             self._grad_dirty = False
         self._mark("start")
-        self.group.pull(ids, out=self.X32)
+        g = self.group
+        v2 = getattr(g, "v2", False) and update
+        side_used = False
+        if v2:
+            if planned:
+                g._armed[0] = (g._key(ids), "prefetch")
+            if next_ids is not None:
+                cur = torch.cuda.current_stream(self.dev)
+                self._ev_fork.record(cur)
+                self._s2.wait_event(self._ev_fork)
+                g.prepare(next_ids, next=True, stream=self._s2.cuda_stream)
+                self._ev_plan.record(self._s2)
+                side_used = True
+            # training pull: gather + plan of this batch in one launch (or a plain gather if the plan was prefetched)
+            g.pull(ids, out=self.X32, train=True)
+        else:
+            g.pull(ids, out=self.X32)
         self._mark("pull")
         tn = self.mn_major
         pa = _PrepArgs(self.X32.data_ptr(), self.XS, self.A0.data_ptr(), 0 if tn else self.A0T.data_ptr(), ids.data_ptr(), self.nf,
@@ -295,6 +315,8 @@ class FusedCTR:
         G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
                   S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
         self._mark("dx_gemm")
+        if side_used:        # the plan(s) built on the side stream are complete before the push reads / flips the slots
+            torch.cuda.current_stream(self.dev).wait_event(self._ev_plan)
         forked = update and self.overlap
         if forked:
             cur = torch.cuda.current_stream(self.dev)
@@ -393,7 +415,14 @@ class FusedCTR:
 
 
 class FusedTrainer:
-    """CUDA-graph driver for ``FusedCTR`` with the same interface as ``models.trainer.Trainer``."""
+    """CUDA-graph driver for ``FusedCTR`` with the same interface as ``models.trainer.Trainer``.
+
+    ``step(ids, dense, labels, next_ids=...)``: with ``next_ids`` (the device ids of the batch that will be passed
+    as ``ids`` to the NEXT call) the de-duplication plan of the next batch is built inside this step on a side
+    stream -- the prefetch of the reference's ``pulling`` (exb.py:645-691)."""
+
+    supports_prefetch = True
+    want_prefetch = False        # set True to let ``make_pipeline`` run one batch ahead and prefetch the plans
 
     def __init__(self, model, use_graph=True):
         self.m, self.ctx = model, model.ctx
@@ -401,25 +430,49 @@ class FusedTrainer:
         self.use_graph = use_graph
         self.graph, self._static = None, None
         self._ar = model._ar
+        self.prefetch = False            # decided at capture time: was the first step given next_ids?
+        self._planned_key = None         # key of the batch whose plan the last step prefetched
 
-    def step(self, ids, dense, labels):
+    def step(self, ids, dense, labels, next_ids=None):
+        g = self.m.group
+        v2 = getattr(g, "v2", False)
+        if not v2:
+            next_ids = None
         if not self.use_graph:
-            loss = self.m.forward_backward(ids, dense, labels)
+            loss = self.m.forward_backward(ids, dense, labels, next_ids=next_ids)
             self.ctx.step_done()
             return loss
         if self.graph is None:
-            self._capture(ids, dense, labels)
+            self._capture(ids, dense, labels, next_ids)
         s = self._static
         if ids.data_ptr() != s["ids"].data_ptr():
             s["ids"].copy_(ids, non_blocking=True)
             s["dense"].copy_(dense, non_blocking=True)
             s["labels"].copy_(labels, non_blocking=True)
+        if self.prefetch:
+            if self._planned_key is None or self._planned_key != g._key(ids):
+                # the current slot does not hold the plan of this batch (first step, or the caller changed its
+                # mind about the next batch): plan it now, eagerly
+                g.prepare(s["ids"], next=False)
+            if next_ids is not None:
+                s["next_ids"].copy_(next_ids, non_blocking=True)
+                self._planned_key = g._key(next_ids)
+            else:
+                self._planned_key = None     # the graph still plans the stale static batch; it is dropped next step
         self.graph.replay()
+        if v2:
+            # replays bypass the plan's python bookkeeping: after the push the current slot holds what the graph
+            # planned as "next" (if anything) under a key no tensor can match -> any eager use re-plans
+            g._armed = [(("graph", id(self)), "pull") if self.prefetch else None, None]
         self.ctx.step_done()
         return s["loss"]
 
-    def _capture(self, ids, dense, labels):
+    def _capture(self, ids, dense, labels, next_ids=None):
         s = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone()}
+        g = self.m.group
+        self.prefetch = next_ids is not None and getattr(g, "v2", False)
+        if self.prefetch:
+            s["next_ids"] = next_ids.clone()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -429,10 +482,15 @@ class FusedTrainer:
         torch.cuda.synchronize(self.device)
         if self.world > 1:
             self.ctx.barrier()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"])
-        self.graph, self._static = g, s
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            if self.prefetch:
+                s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"], next_ids=s["next_ids"], planned=True)
+            else:
+                s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+        if getattr(g, "v2", False):
+            g._armed = [None, None]      # capture only recorded launches: no slot is armed on the device
+        self.graph, self._static = gr, s
 
     def make_pipeline(self, batch, num_sparse, num_dense):
         from .trainer import _Pipeline

@@ -118,46 +118,77 @@ class Trainer:
 
 
 class _Pipeline:
-    """Double-buffered user-facing step: ``submit(host_ids, host_dense, host_labels)``
-    enqueues H2D on a copy stream, the graph on the compute stream and an async D2H of
-    the loss; ``losses()`` returns what has completed. Inputs must be pinned."""
+    """User-facing end-to-end step: ``submit(host_ids, host_dense, host_labels)`` enqueues the H2D copy on a copy
+    stream, one training step on the compute stream and an asynchronous D2H of its loss; ``last_loss()`` drains.
+    Inputs must be pinned.
+
+    With a trainer that can prefetch (``FusedTrainer``: ``step(..., next_ids=)``) the pipeline runs ONE BATCH
+    AHEAD: ``submit(batch k)`` copies batch k and trains batch k-1 with ``next_ids`` = the device ids of batch k,
+    so the de-duplication plan of batch k is built while batch k-1 computes -- the reference's ``pulling``
+    input-pipeline prefetch (exb.py:645-691). Three device buffers: the copy of batch k+1 overlaps step k-1."""
+
+    NBUF = 3
 
     def __init__(self, trainer, batch, num_sparse, num_dense):
         self.t = trainer
         dev = trainer.device
+        n = self.NBUF
+        self.lookahead = bool(getattr(trainer, "supports_prefetch", False)) and bool(getattr(trainer, "want_prefetch", False))
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.dev = [dict(ids=torch.zeros((batch, num_sparse), dtype=torch.int64, device=dev),
                          dense=torch.zeros((batch, num_dense), dtype=torch.float32, device=dev),
-                         labels=torch.zeros((batch,), dtype=torch.float32, device=dev)) for _ in range(2)]
-        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
-        self.done = [torch.cuda.Event() for _ in range(2)]
-        self.k = 0
+                         labels=torch.zeros((batch,), dtype=torch.float32, device=dev)) for _ in range(n)]
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.copied = [torch.cuda.Event() for _ in range(n)]
+        self.consumed = [torch.cuda.Event() for _ in range(n)]
+        self.done = [torch.cuda.Event() for _ in range(n)]
+        self.k = 0            # batches submitted
+        self.trained = 0      # batches trained
         self.h2d_bytes = batch * num_sparse * 8 + batch * num_dense * 4 + batch * 4
         self.d2h_bytes = 4
 
-    def submit(self, ids_h, dense_h, labels_h):
-        i = self.k & 1
+    def _train(self, j, next_ids):
+        """launch the step of batch j (device buffer j % NBUF)"""
+        i = j % self.NBUF
         cur = torch.cuda.current_stream(self.t.device)
-        if self.k >= 2:
-            self.copy_stream.wait_event(self.consumed[i])     # buffer i free again
+        cur.wait_event(self.copied[i])
+        if j >= self.NBUF:
+            self.done[i].synchronize()                        # loss_host[i] of batch j - NBUF has landed
+        d = self.dev[i]
+        if next_ids is not None:
+            loss = self.t.step(d["ids"], d["dense"], d["labels"], next_ids=next_ids)
+        else:
+            loss = self.t.step(d["ids"], d["dense"], d["labels"])
+        self.consumed[i].record(cur)
+        self.loss_host[i].copy_(loss, non_blocking=True)
+        self.done[i].record(cur)
+        self.trained = j + 1
+
+    def submit(self, ids_h, dense_h, labels_h):
+        k = self.k
+        i = k % self.NBUF
+        if k >= self.NBUF:
+            self.copy_stream.wait_event(self.consumed[i])     # buffer i free again (batch k - NBUF trained)
         with torch.cuda.stream(self.copy_stream):
             d = self.dev[i]
             d["ids"].copy_(ids_h, non_blocking=True)
             d["dense"].copy_(dense_h, non_blocking=True)
             d["labels"].copy_(labels_h, non_blocking=True)
             self.copied[i].record(self.copy_stream)
-        cur.wait_event(self.copied[i])
-        if self.k >= 2:
-            self.done[i].synchronize()                        # loss_host[i] of step k-2 has landed
-        loss = self.t.step(self.dev[i]["ids"], self.dev[i]["dense"], self.dev[i]["labels"])
-        self.consumed[i].record(cur)
-        self.loss_host[i].copy_(loss, non_blocking=True)
-        self.done[i].record(cur)
-        self.k += 1
+        self.k = k + 1
+        if not self.lookahead:
+            self._train(k, None)
+        elif k >= 1:
+            cur = torch.cuda.current_stream(self.t.device)
+            cur.wait_event(self.copied[i])                    # the plan kernel of batch k reads its ids
+            self._train(k - 1, self.dev[i]["ids"])
+
+    def flush(self):
+        while self.trained < self.k:
+            self._train(self.trained, None)
 
     def last_loss(self):
-        i = (self.k - 1) & 1
+        self.flush()
+        i = (self.k - 1) % self.NBUF
         self.done[i].synchronize()
         return float(self.loss_host[i])

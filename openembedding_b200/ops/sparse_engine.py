@@ -182,18 +182,23 @@ class CudaEngine:
         st = ctypes.c_int32(0)
         stats = _u64arr(32)
         _native.cuda_check(self.lib.exb_engine_status(self.h, ctypes.byref(st), stats), "status")
-        t = [int(stats[8 + i]) for i in range(7)]
-        names = ["dispatch", "barrier_publish", "combine", "barrier_acc", "apply", "barrier_done"]
+        v2 = int(stats[7]) == 2          # which push kernel stamped the phase clock last
+        nst = 8 if v2 else 7
+        t = [int(stats[8 + i]) for i in range(nst)]
+        names = (["reduce", "dispatch", "barrier_publish", "combine", "barrier_acc", "apply", "barrier_done"] if v2
+                 else ["dispatch", "barrier_publish", "combine", "barrier_acc", "apply", "barrier_done"])
         phases = {}
-        if t[0] and t[6] >= t[0]:
+        if t[0] and t[nst - 1] >= t[0]:
             prev = t[0]
             for i, nm in enumerate(names):
-                cur = t[i + 1] if t[i + 1] else prev     # phases skipped at world==1 keep the clock
+                cur = t[i + 1] if t[i + 1] >= prev else prev     # phases skipped at world==1 keep the clock
                 phases[nm] = (cur - prev) / 1e3
                 prev = cur
-            phases["total"] = (t[6] - t[0]) / 1e3
+            phases["total"] = (t[nst - 1] - t[0]) / 1e3
         return int(st.value), {"pull_indices": int(stats[0]), "push_indices": int(stats[1]),
-                               "update_unique": int(stats[2]), "last_push_update_us": phases,
+                               "update_unique": int(stats[2]), "plans": int(stats[3]), "pull_unique": int(stats[4]),
+                               "nvlink_rows_pulled": int(stats[5]), "nvlink_rows_pushed": int(stats[6]),
+                               "last_push_update_us": phases,
                                "probe": [int(stats[i]) for i in range(16, 28)]}
 
     def _raise(self, code):
@@ -221,7 +226,7 @@ class CudaEngine:
         if not self._st_pending:
             if self._st_dev is None:
                 from .p2p_allreduce import tensor_from_ptr
-                self._st_dev = tensor_from_ptr(self.lib.exb_engine_sync_ptr(self.h) + 132, 1, self.device,
+                self._st_dev = tensor_from_ptr(self.lib.exb_engine_status_ptr(self.h), 1, self.device,
                                                dtype=torch.int32)
             with torch.cuda.stream(self._st_stream):
                 self._st_host.copy_(self._st_dev, non_blocking=True)
@@ -310,6 +315,14 @@ class SparsePlan:
         if not self.h:
             raise RuntimeError("exb_plan_create: " + self.lib.exb_cuda_last_error().decode())
         self.connected = engine.world == 1
+        # v2 ("plan once per step", csrc/cuda/sparse_v2.cuh): ids are de-duplicated once per batch into one of two
+        # batch slots; pull moves unique remote rows, push moves pre-reduced rows. EXB_SPARSE_V2=0: v1 kernels.
+        self.v2 = os.environ.get("EXB_SPARSE_V2", "1") != "0"
+        # EXB_PULL2=1: training pulls of world > 1 move UNIQUE remote rows (exb_pull2_kernel: gather unique rows,
+        # grid barrier, expand). Measured slower than the one-pass gather on 2 and 8 B200s (the step is bound by the
+        # number of dependent phases, not by NVLink bytes -- profiles/r2/sparse_v2.md), hence off by default.
+        self.pull2 = os.environ.get("EXB_PULL2", "0") == "1"
+        self._armed = [None, None]       # relative slots (0 current, 1 next): ((ids ptr, n), origin) or None
         engine.plans.append(self)
         if engine.world == 1:
             engine.commit()
@@ -323,20 +336,81 @@ class SparsePlan:
     def _stream(self):
         return torch.cuda.current_stream(self.e.device).cuda_stream
 
-    def pull(self, ids, out=None):
-        """ids [n, ncols] int64 (cuda, contiguous) -> out [n, io_stride] fp32."""
+    # ---- v2 slot bookkeeping (mirrors the device-side parity word: push_update flips current <-> next)
+    @staticmethod
+    def _key(ids):
+        return (ids.data_ptr(), ids.shape[0])
+
+    def reset_slot(self, which=0):
+        """drop a prepared batch that will not be pushed"""
+        _native.cuda_check(self.lib.exb_plan_reset(self.h, which, self._stream()), "plan_reset")
+        self._armed[which] = None
+
+    def prepare(self, ids, next=False, stream=None):
+        """De-duplicate the ids of a batch into a batch slot (ids only, no table access).
+
+        ``next=True`` is the PREFETCH of the reference (``pulling`` / PrefetchPullWeights): the plan of batch
+        k+1 is built -- typically on a side stream -- while batch k trains; after the ``push_update`` of batch k
+        that slot becomes the current one and ``pull(train=True)`` / ``push_update`` of batch k+1 find their plan
+        ready. The ids tensor must stay unchanged until that push."""
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape[1] == self.ncols
+        which = 1 if next else 0
+        if self._armed[which] is not None:
+            self.reset_slot(which)
+        st = stream if stream is not None else self._stream()
+        _native.cuda_check(self.lib.exb_plan_prepare(self.h, ids.data_ptr(), ids.shape[0], which, st), "plan_prepare")
+        self._armed[which] = (self._key(ids), "prefetch" if next else "pull")
+
+    def _ensure(self, ids, for_push):
+        a = self._armed[0]
+        if a is not None and a[0] == self._key(ids) and (for_push or a[1] == "prefetch"):
+            return
+        self.prepare(ids, next=False)
+
+    def pull(self, ids, out=None, train=False):
+        """ids [n, ncols] int64 (cuda, contiguous) -> out [n, io_stride] fp32.
+
+        ``train=True`` announces that ``push_update`` of the same ids follows: the batch is planned (or its
+        prefetched plan is used) and, with world > 1, only UNIQUE remote rows cross NVLink. ``train=False``
+        is the stateless read (evaluation, export, serving)."""
         assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape[1] == self.ncols
         n = ids.shape[0]
         if out is None:
             out = torch.empty((n, self.io_stride), dtype=torch.float32, device=ids.device)
+        if self.v2 and train:
+            if self.pull2 and self.e.world > 1:
+                self._ensure(ids, for_push=False)
+                _native.cuda_check(self.lib.exb_pull2(self.h, ids.data_ptr(), out.data_ptr(), n, 0, self._stream()), "pull2")
+                return out
+            a = self._armed[0]
+            if not (a is not None and a[0] == self._key(ids) and a[1] == "prefetch"):
+                # one launch: gather (6 warps per CTA) + de-duplication plan of the batch (2 warps per CTA)
+                if a is not None:
+                    self.reset_slot(0)
+                _native.cuda_check(self.lib.exb_pull_plan(self.h, ids.data_ptr(), out.data_ptr(), n, 0, self._stream()),
+                                   "pull_plan")
+                self._armed[0] = (self._key(ids), "pull")
+                return out
+            # the plan was prefetched: plain gather
         _native.cuda_check(self.lib.exb_pull(self.h, ids.data_ptr(), out.data_ptr(), n, self._stream()), "pull")
         return out
 
     def push_update(self, ids, grads):
         assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous()
         assert grads.dtype == torch.float32 and grads.is_contiguous() and grads.shape[1] == self.io_stride
-        _native.cuda_check(self.lib.exb_push_update(self.h, ids.data_ptr(), grads.data_ptr(), ids.shape[0],
-                                                    self._stream()), "push_update")
+        if not self.v2:
+            _native.cuda_check(self.lib.exb_push_update(self.h, ids.data_ptr(), grads.data_ptr(), ids.shape[0],
+                                                        self._stream()), "push_update")
+            return
+        self._ensure(ids, for_push=True)
+        _native.cuda_check(self.lib.exb_push2(self.h, grads.data_ptr(), ids.shape[0], 0, self._stream()), "push2")
+        self._armed = [self._armed[1], None]          # the kernel flipped the parity word
+
+    def memory(self):
+        """bytes of device memory held by the plan: (peer-visible inbox, local work area of both slots)"""
+        out = _u64arr(2)
+        self.lib.exb_plan_memory(self.h, out)
+        return int(out[0]), int(out[1])
 
     def grid(self):
         return self.lib.exb_plan_grid(self.h, 0), self.lib.exb_plan_grid(self.h, 1)

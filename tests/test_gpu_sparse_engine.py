@@ -34,8 +34,11 @@ def _oracle_pull(lib, h, ids, dim):
     return out
 
 
-def _run(world, specs, batch, steps, opt_cfg, init_cfg, seed=0):
-    """specs: list of (dim, vocab, is_hash). Returns max abs error vs oracle after `steps`."""
+def _run(world, specs, batch, steps, opt_cfg, init_cfg, seed=0, mode="stateless"):
+    """specs: list of (dim, vocab, is_hash). Returns max abs error vs oracle after `steps`.
+    mode: "stateless" -- pull(train=False) + push_update (the push plans the batch itself);
+          "train"     -- pull(train=True): planned batch, unique remote rows (exb_pull2_kernel at world > 1);
+          "prefetch"  -- like train, and the plan of step s+1 is built with prepare(next=True) during step s."""
     from openembedding_b200.ops.sparse_engine import CudaEngine
     torch.manual_seed(seed)
     dev = torch.device("cuda", 0)
@@ -54,8 +57,9 @@ def _run(world, specs, batch, steps, opt_cfg, init_cfg, seed=0):
     streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
     sl = plans[0].feature_slices()
     worst = 0.0
+    all_ids = []
     for step in range(steps):
-        ids, grads, outs = [], [], []
+        row = []
         for r in range(world):
             cols = []
             for (dim, vocab, is_hash) in specs:
@@ -64,13 +68,19 @@ def _run(world, specs, batch, steps, opt_cfg, init_cfg, seed=0):
                 if is_hash:
                     c = c * 1000003 + 7          # sparse keys in a huge space
                 cols.append(c)
-            ids.append(torch.stack(cols, dim=1).contiguous().to(dev))
+            row.append(torch.stack(cols, dim=1).contiguous().to(dev))
+        all_ids.append(row)
+    for step in range(steps):
+        ids, grads, outs = all_ids[step], [], []
+        for r in range(world):
             grads.append(torch.randn(batch, plans[r].io_stride, device=dev))
         torch.cuda.synchronize()
         # --- pull on every rank and compare with the oracle BEFORE the update
         for r in range(world):
             with torch.cuda.stream(streams[r]):
-                outs.append(plans[r].pull(ids[r]))
+                outs.append(plans[r].pull(ids[r], train=(mode != "stateless")))
+                if mode == "prefetch" and step + 1 < steps:
+                    plans[r].prepare(all_ids[step + 1][r], next=True)
         torch.cuda.synchronize()
         for r in range(world):
             for f, (dim, vocab, is_hash) in enumerate(specs):
@@ -137,6 +147,58 @@ def test_virtual_ranks(world):
     specs = [(64, 100000, False), (1, 100000, False), (9, 3, False), (16, 0, True), (4, 77, False)]
     err = _run(world, specs, batch=192, steps=3, opt_cfg=ADAGRAD, init_cfg=UNIFORM)
     assert err < 5e-4, err
+
+
+@pytest.mark.parametrize("world,mode", [(1, "train"), (1, "prefetch"), (2, "train"), (3, "prefetch"), (4, "train"),
+                                        (8, "prefetch")])
+def test_planned_batches(world, mode):
+    """v2 path end to end: de-duplicated plan, unique-row pull (exb_pull2_kernel), pre-reduced push, prefetch"""
+    specs = [(64, 100000, False), (1, 100000, False), (9, 3, False), (16, 0, True), (4, 77, False), (200, 50, False)]
+    err = _run(world, specs, batch=192, steps=4, opt_cfg=ADAGRAD, init_cfg=UNIFORM, mode=mode)
+    assert err < 5e-4, err
+
+
+def test_planned_test_optimizer_counts():
+    """the `test` optimizer consumes the per-id counts: they must survive de-duplication and pre-reduction"""
+    cfg = {"category": "test", "learning_rate": 0.05}
+    err = _run(2, [(16, 300, False), (8, 0, True)], batch=128, steps=4, opt_cfg=cfg, init_cfg=UNIFORM, mode="train")
+    assert err < 5e-3, err
+
+
+def test_v1_kernels_still_match(monkeypatch):
+    monkeypatch.setenv("EXB_SPARSE_V2", "0")
+    specs = [(64, 100000, False), (1, 100000, False), (16, 0, True)]
+    err = _run(2, specs, batch=192, steps=3, opt_cfg=ADAGRAD, init_cfg=UNIFORM)
+    assert err < 5e-4, err
+
+
+def test_abandoned_plan_is_reset():
+    """a planned batch that is never pushed (evaluation under grad mode) must not leak into the next batch"""
+    from openembedding_b200.ops.sparse_engine import CudaEngine
+    dev = torch.device("cuda", 0)
+    e = CudaEngine(0, 0, 1)
+    t = e.add_table(8, 1000, False)
+    e.set_initializer(t, {"category": "constant", "value": 0.0}, 0)
+    e.set_optimizer(t, {"category": "sgd", "learning_rate": 1.0})
+    e.alloc(t)
+    plan = e.make_plan([t], 256)
+    a = torch.arange(0, 256, dtype=torch.int64, device=dev).reshape(-1, 1) % 7
+    b = (torch.arange(0, 256, dtype=torch.int64, device=dev).reshape(-1, 1) % 5) + 100
+    plan.pull(a, train=True)                  # planned, never pushed
+    plan.prepare(b, next=True)                # prefetched, never used
+    g = torch.ones(256, plan.io_stride, device=dev)
+    plan.pull(b, train=True)
+    plan.push_update(b, g)                    # must update ids 100..104 only
+    plan.push_update(a, g)
+    torch.cuda.synchronize()
+    e.check()
+    probe = torch.tensor([[0], [6], [7], [100], [104], [105]], dtype=torch.int64, device=dev)
+    out = plan.pull(probe)[:, 0].cpu()
+    want = torch.tensor([-37.0, -36.0, 0.0, -52.0, -51.0, 0.0])    # 256 lookups over 7 / 5 ids, sgd lr 1
+    assert torch.equal(out, want), out
+    st = e.status()[1]
+    assert st["pull_unique"] == 12, st
+    e.close()
 
 
 def test_hot_rows_many_duplicates():

@@ -1,0 +1,17 @@
+#!/bin/bash
+# N-GPU call: multi-GPU pytest + bench v2 / v1 / baseline at N = $1
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_pytest_mp_n$N.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r2_pytest_mp_n$N.log
+run() { # name, extra env/args...
+  name=$1; shift
+  timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 300 --warmup 20 $EXTRA > gpurun_out/r2_bench_${name}_n$N.log 2>&1
+  echo "$name rc=$?"
+  grep '^{' gpurun_out/r2_bench_${name}_n$N.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d.get('push_update_phases_us'), d.get('sparse_counters'))"
+}
+EXTRA="" run v2 EXB_SPARSE_V2=1
+EXTRA="--prefetch" run v2pf EXB_SPARSE_V2=1
+EXTRA="" run v1 EXB_SPARSE_V2=0
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --impl baseline --steps 100 --warmup 10 > gpurun_out/r2_bench_base_n$N.log 2>&1; echo "base rc=$?"
+grep '^{' gpurun_out/r2_bench_base_n$N.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"
