@@ -336,6 +336,8 @@ def main():
             "native_libs": {"cuda": _native.cuda_loaded()},
             "final_loss": loss_val, "e2e_final_loss": e2e_loss,
             "push_update_phases_us": ctx.backend.engine.status()[1].get("last_push_update_us"),
+            "pull_probe_us": [round((x - ctx.backend.engine.status()[1]["probe"][0]) / 1e3, 2) if x else None
+                              for x in ctx.backend.engine.status()[1]["probe"][:8]],
             "sparse_counters": {k: v for k, v in ctx.backend.engine.status()[1].items()
                                 if k in ("pull_indices", "pull_unique", "push_indices", "update_unique",
                                          "nvlink_rows_pulled", "nvlink_rows_pushed", "plans")},

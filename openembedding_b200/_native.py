@@ -117,6 +117,7 @@ def cuda():
         P(lib, "exb_ipc_close_handle", c_int, [c_uint64])
         P(lib, "exb_enable_peer_access", c_int, [c_int, c_int])
         P(lib, "exb_plan_create", c_void_p, [c_void_p, c_int, i32p, i32p, i32p, c_int, c_int, c_int])
+        P(lib, "exb_plan_create2", c_void_p, [c_void_p, c_int, i32p, i32p, i32p, c_int, c_int, c_int, i32p, i32p])
         P(lib, "exb_plan_destroy", None, [c_void_p])
         P(lib, "exb_plan_inbox_info", c_int, [c_void_p, u64p])
         P(lib, "exb_plan_set_peer_inbox", c_int, [c_void_p, c_int, c_uint64])

@@ -70,6 +70,157 @@ __device__ __forceinline__ void pull_rows_bulk(const TableDev& T, const float* s
     }
 }
 
+// Single-pass pull of a warp task: columns [0, bulk) of the 32 rows are gathered with cp.async through the warp's
+// buffer, the remaining (< 8) columns of row l by lane l into registers -- so a [D | 1] split row of D = 64 needs
+// the same 8 KB as a plain 64-column row and never a second pass. `mid()` runs while the loads are in flight
+// (the training pull builds the batch's de-duplication plan there). Requires 32 * bulk * 4 <= EXB_PULL_WARP_BUF.
+//   split >= dim: not a split feature (bulk = wstride); else columns [split, dim) go to out[b, off2 ...].
+// LPR (lanes per row of the bulk part, power of two >= bulk / 4) is a template parameter: every loop below has a
+// compile-time trip count and unrolls -- the run-time form executed ~1300 instructions per warp task, and a warp
+// task is one dependent chain (ncu: profiles/r2/pull_plan_ncu.md).
+template <int LPR, class Mid>
+__device__ __forceinline__ void pull_rows_fast_t(const TableDev& T, const float* src, unsigned long long id, int flag,
+                                                 int b0, int n_rows, float* __restrict__ out, int io_stride, int off,
+                                                 int off2, int split, int bulk, int lane, unsigned char* buf, Mid mid) {
+    constexpr int RP = 32 / LPR;
+    const int wstride = T.wstride, dim = T.dim;
+    const int gl = lane % LPR, sub = lane / LPR;
+    const int c = gl * 4;
+    const bool cin = c < bulk;
+    float* rows = reinterpret_cast<float*>(buf);
+#pragma unroll
+    for (int jb = 0; jb < 32; jb += RP) {
+        const int j = jb + sub;
+        const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, j);
+        const int fl = __shfl_sync(0xffffffffu, flag, j);
+        if (fl == 1 && cin) cp_async16(rows + (size_t)j * bulk + c, s + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float4 tl[2];
+    tl[0] = tl[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ntail = (wstride - bulk) >> 2;           // 0, 1 or 2 float4 per row
+    if (flag == 1) {
+        if (ntail > 0) tl[0] = ld_stream_v4(src + bulk);
+        if (ntail > 1) tl[1] = ld_stream_v4(src + bulk + 4);
+    } else if (flag == 2) {
+        if (ntail > 0) tl[0] = init_block_masked(&T.init, id, bulk, dim);
+        if (ntail > 1) tl[1] = init_block_masked(&T.init, id, bulk + 4, dim);
+    }
+    mid();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const unsigned any2 = __ballot_sync(0xffffffffu, flag == 2);
+#pragma unroll
+    for (int jb = 0; jb < 32; jb += RP) {
+        const int j = jb + sub;
+        const int fl = __shfl_sync(0xffffffffu, flag, j);
+        const int b = b0 + j;
+        if (b >= n_rows || !cin) continue;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fl == 1) v = *reinterpret_cast<const float4*>(rows + (size_t)j * bulk + c);
+        *reinterpret_cast<float4*>(out + (size_t)b * io_stride + off + c) = v;
+    }
+    if (any2) {                                        // rows answered with their initializer value (cold)
+        for (int j = 0; j < 32; ++j) {
+            if (!((any2 >> j) & 1u)) continue;
+            const unsigned long long idr = __shfl_sync(0xffffffffu, id, j);
+            if (b0 + j < n_rows)
+                for (int cc = lane * 4; cc < bulk; cc += 128)
+                    *reinterpret_cast<float4*>(out + (size_t)(b0 + j) * io_stride + off + cc) = init_block_masked(&T.init, idr, cc, dim);
+        }
+    }
+    if (ntail > 0 && b0 + lane < n_rows) {             // lane l finishes row l
+        float* dst = out + (size_t)(b0 + lane) * io_stride + off;
+        float* dst2 = out + (size_t)(b0 + lane) * io_stride + off2;
+        const float t[8] = {tl[0].x, tl[0].y, tl[0].z, tl[0].w, tl[1].x, tl[1].y, tl[1].z, tl[1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = bulk + e;
+            if (e < 4 * ntail) {
+                if (col < split) { if (col < wstride) dst[col] = t[e]; }
+                else if (col < dim) dst2[col - split] = t[e];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <class Mid>
+__device__ __forceinline__ void pull_rows_fast(const TableDev& T, const float* src, unsigned long long id, int flag,
+                                               int b0, int n_rows, float* __restrict__ out, int io_stride, int off,
+                                               int off2, int split, int bulk, int lane, unsigned char* buf, Mid mid) {
+    const int chunks = bulk >> 2;
+#define EXB_PRF(L) pull_rows_fast_t<L>(T, src, id, flag, b0, n_rows, out, io_stride, off, off2, split, bulk, lane, buf, mid)
+    if (chunks <= 1) EXB_PRF(1);
+    else if (chunks <= 2) EXB_PRF(2);
+    else if (chunks <= 4) EXB_PRF(4);
+    else if (chunks <= 8) EXB_PRF(8);
+    else if (chunks <= 16) EXB_PRF(16);
+    else EXB_PRF(32);
+#undef EXB_PRF
+}
+// column split of pull_rows_fast for a feature: bulk columns and whether the single-pass form applies
+__device__ __forceinline__ bool pull_fast_geometry(const TableDev& T, int split, int* bulk) {
+    const bool is_split = split < T.dim;
+    *bulk = is_split ? (split & ~3) : T.wstride;
+    if (!T.vec4 || *bulk <= 0) return false;
+    if (T.wstride - *bulk > 8 || *bulk > 128) return false;
+    return 32 * (*bulk) * 4 <= (int)EXB_PULL_WARP_BUF;
+}
+
+// Split-row feature: ONE table row feeds two places of the activation row -- columns [0, split) go to
+// out[b, off ...], columns [split, dim) to out[b, off2 ...] (e.g. DeepFM: the dim-D embedding and the dim-1
+// linear weight of a sparse feature share one row of dim D+1, so one lookup / one unique id / one optimizer
+// row serves both; the reference keeps them as two variables = two RPCs, criteo_deepctr.py:60-110).
+// Same cp.async gather as pull_rows_bulk; only the write-out differs. Pad columns are not written.
+__device__ __forceinline__ void pull_rows_split(const TableDev& T, const float* src, unsigned long long id,
+                                                int flag, int b0, int n_rows, float* __restrict__ out,
+                                                int io_stride, int off, int off2, int split, int lane,
+                                                unsigned char* buf) {
+    const int wstride = T.wstride, dim = T.dim;
+    const unsigned rowbytes = (unsigned)wstride * 4u;
+    const int R = min(32, (int)(EXB_PULL_WARP_BUF / rowbytes));
+    const int lpr = T.lpr, gl = lane % lpr, RP = 32 / lpr;
+    float* rows = reinterpret_cast<float*>(buf);
+    for (int r0 = 0; r0 < 32; r0 += R) {
+        for (int jb = 0; jb < R; jb += RP) {
+            const int j = jb + lane / lpr, r = r0 + j;
+            const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r & 31);
+            const int fl = __shfl_sync(0xffffffffu, flag, r & 31);
+            if (j < R && r < 32 && fl == 1)
+                for (int c = gl * 4; c < wstride; c += lpr * 4) cp_async16(rows + (size_t)j * wstride + c, s + c);
+        }
+        cp_async_commit_wait();
+        __syncwarp();
+        for (int jb = 0; jb < R; jb += RP) {
+            const int j = jb + lane / lpr, r = r0 + j;
+            const unsigned long long idr = __shfl_sync(0xffffffffu, id, r & 31);
+            const int fl = __shfl_sync(0xffffffffu, flag, r & 31);
+            const int b = b0 + r;
+            if (j >= R || r >= 32 || b >= n_rows) continue;
+            float* dst = out + (size_t)b * io_stride + off;
+            float* dst2 = out + (size_t)b * io_stride + off2;
+            for (int c = gl * 4; c < wstride; c += lpr * 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fl == 1) v = *reinterpret_cast<const float4*>(rows + (size_t)j * wstride + c);
+                else if (fl == 2) v = init_block_masked(&T.init, idr, c, dim);
+                if (c + 4 <= split) {
+                    *reinterpret_cast<float4*>(dst + c) = v;
+                } else {
+                    const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = c + e;
+                        if (col < split) dst[col] = t[e];
+                        else if (col < dim) dst2[col - split] = t[e];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 struct WarpMeta {   // per-warp row metadata of the apply phase (shared memory)
     unsigned long long key[32];
     unsigned long long row[32];

@@ -607,8 +607,9 @@ int exb_enable_peer_access(int device, int peer_device) {
 }
 
 // ---- plans
-void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off, const int* feat_col, int ncols,
-                      int B, int io_stride) {
+// feat_off2 / feat_split (both may be null): split-row features, see pull_rows_split in bulk_rows.cuh
+void* exb_plan_create2(void* h, int F, const int* feat_table, const int* feat_off, const int* feat_col, int ncols,
+                       int B, int io_stride, const int* feat_off2, const int* feat_split) {
     Engine* e = (Engine*)h;
     CKP(cudaSetDevice(e->device));
     const int W = e->world;
@@ -622,6 +623,14 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     }
     const int PT = (int)pt_table.size();
     if (PT > 128 || W * PT > EXB_MAX_SEG) { fail_msg("plan: too many tables for one plan (max 128)"); return nullptr; }
+    std::vector<int> off2(F, 0), split(F, 0x7fffffff);
+    for (int f = 0; f < F; ++f) {
+        if (!feat_split || !feat_off2) break;
+        const TableDev& T = e->tables[feat_table[f]].d;
+        if (feat_split[f] <= 0 || feat_split[f] >= T.dim) continue;
+        if (!T.vec4 || T.wstride * 4 > (int)EXB_PULL_WARP_BUF) { fail_msg("plan: a split-row feature needs 4 <= dim <= 2048"); return nullptr; }
+        off2[f] = feat_off2[f]; split[f] = feat_split[f];
+    }
     Plan* p = new Plan();
     p->e = e;
     PlanDev& d = p->d;
@@ -648,13 +657,14 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     // ---- meta buffer
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
-    size_t o_feat_col = take(F * 4);
+    size_t o_feat_col = take(F * 4), o_feat_off2 = take(F * 4), o_feat_split = take(F * 4);
     size_t o_feat_pt = take(F * 4), o_feat_off = take(F * 4), o_prefix = take((F + 1) * 4), o_pt_table = take(PT * 4),
            o_cap = take(PT * 4), o_koff = take(PT * 8), o_goff = take(PT * 8), o_moff = take(PT * 8),
            o_mask = take(PT * 4), o_aoff = take(PT * 8), o_uoff = take(PT * 8);
     std::vector<char> hm(off);
     memcpy(&hm[o_feat_pt], feat_pt.data(), F * 4); memcpy(&hm[o_feat_off], feat_off, F * 4);
     memcpy(&hm[o_feat_col], feat_col, F * 4);
+    memcpy(&hm[o_feat_off2], off2.data(), F * 4); memcpy(&hm[o_feat_split], split.data(), F * 4);
     memcpy(&hm[o_prefix], task_prefix.data(), (F + 1) * 4); memcpy(&hm[o_pt_table], pt_table.data(), PT * 4);
     memcpy(&hm[o_cap], pt_cap.data(), PT * 4); memcpy(&hm[o_koff], key_off.data(), PT * 8);
     memcpy(&hm[o_goff], grad_off.data(), PT * 8); memcpy(&hm[o_moff], map_off.data(), PT * 8);
@@ -664,6 +674,7 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     CKP(cudaMemcpy(p->meta, hm.data(), off, cudaMemcpyHostToDevice));
     d.feat_pt = (const int*)(p->meta + o_feat_pt); d.feat_off = (const int*)(p->meta + o_feat_off);
     d.feat_col = (const int*)(p->meta + o_feat_col);
+    d.feat_off2 = (const int*)(p->meta + o_feat_off2); d.feat_split = (const int*)(p->meta + o_feat_split);
     d.task_prefix = (const int*)(p->meta + o_prefix); d.pt_table = (const int*)(p->meta + o_pt_table);
     d.pt_cap = (const unsigned*)(p->meta + o_cap);
     d.pt_key_off = (const unsigned long long*)(p->meta + o_koff);
@@ -767,6 +778,10 @@ void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off
     CKP(cudaDeviceSynchronize());
     return p;
 }
+void* exb_plan_create(void* h, int F, const int* feat_table, const int* feat_off, const int* feat_col, int ncols,
+                      int B, int io_stride) {
+    return exb_plan_create2(h, F, feat_table, feat_off, feat_col, ncols, B, io_stride, nullptr, nullptr);
+}
 void exb_plan_destroy(void* ph) {
     Plan* p = (Plan*)ph;
     cudaSetDevice(p->e->device);
@@ -847,9 +862,7 @@ int exb_pull_plan(void* ph, uint64_t ids, uint64_t out, int n_rows, int which, u
     Plan* p = (Plan*)ph;
     Engine* e = p->e;
     if (n_rows > p->d.B) return fail_msg("pull: n_rows exceeds plan batch");
-    int grid = std::max(1, std::min(p->grid_pull * 8 / EXB_PP_GATHER_WARPS + 1, e->sms * 3));
-    if (e->max_ctas > 0) grid = std::min(grid, e->max_ctas);
-    CK(launch_pdl(exb_pull_plan_kernel, dim3(grid), dim3(256), p->smem_pull, (cudaStream_t)stream,
+    CK(launch_pdl(exb_pull_plan_kernel, dim3(p->grid_pull), dim3(256), p->smem_pull, (cudaStream_t)stream,
                   (const TableDev*)e->d_tables, p->d, (const long long*)ids, (float*)out, n_rows, which));
     return 0;
 }

@@ -60,6 +60,8 @@ struct PlanDev {
     const int* feat_pt;     // [F] feature -> plan-table
     const int* feat_off;    // [F] column offset of the feature in out / grad rows
     const int* feat_col;    // [F] id column of the feature
+    const int* feat_off2;   // [F] split-row features: columns >= feat_split[f] of the table row live at this offset
+    const int* feat_split;  // [F] first column that goes to feat_off2 (>= row width: the feature is not split)
     const int* task_prefix; // [F+1]
     const int* pt_table;    // [PT] plan-table -> engine table id
     const unsigned* pt_cap; // [PT] max entries one source can send for this table per step

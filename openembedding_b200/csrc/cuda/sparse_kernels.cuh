@@ -46,12 +46,14 @@ struct SmemView {
     int* feat_pt;                  // [F]
     int* feat_off;                 // [F]
     int* feat_col;                 // [F]
+    int* feat_off2;                // [F]
+    int* feat_split;               // [F]
     int* seg_prefix;               // [EXB_MAX_SEG+1] (push kernel only)
 };
 
 __host__ __device__ inline size_t exb_smem_bytes(int PT, int F, bool push) {
     size_t b = (size_t)PT * sizeof(TableDev) + (size_t)PT * 8 * 5 + (size_t)PT * 4 * 2 +
-               (size_t)(F + 1) * 4 + (size_t)F * 4 * 3;
+               (size_t)(F + 1) * 4 + (size_t)F * 4 * 5;
     if (push) b += (EXB_MAX_SEG + 1) * 4;
     return (b + 127) & ~(size_t)127;
 }
@@ -81,6 +83,8 @@ __device__ __forceinline__ SmemView stage_plan(const TableDev* __restrict__ tabl
     S.feat_pt = (int*)p; p += F * 4;
     S.feat_off = (int*)p; p += F * 4;
     S.feat_col = (int*)p; p += F * 4;
+    S.feat_off2 = (int*)p; p += F * 4;
+    S.feat_split = (int*)p; p += F * 4;
     S.seg_prefix = (int*)p;
     constexpr int TW = sizeof(TableDev) / 4;
     for (int i = threadIdx.x; i < PT * TW; i += blockDim.x) {
@@ -95,6 +99,7 @@ __device__ __forceinline__ SmemView stage_plan(const TableDev* __restrict__ tabl
     for (int i = threadIdx.x; i <= F; i += blockDim.x) S.task_prefix[i] = P.task_prefix[i];
     for (int i = threadIdx.x; i < F; i += blockDim.x) {
         S.feat_pt[i] = P.feat_pt[i]; S.feat_off[i] = P.feat_off[i]; S.feat_col[i] = P.feat_col[i];
+        S.feat_off2[i] = P.feat_off2[i]; S.feat_split[i] = P.feat_split[i];
     }
     __syncthreads();
     return S;
@@ -179,6 +184,64 @@ __device__ __forceinline__ void pull_rows(const TableDev& T, const float* src, u
     }
 }
 
+// every row shape the single-pass form does not cover (rows wider than the warp buffer / 32, dim < 4, multi-pass
+// split rows). Out of line on purpose: these paths hold 8 float4 of rows in registers per lane group and would
+// otherwise set the register budget (and the spills) of the whole kernel.
+__device__ __noinline__ void pull_rows_slow(const TableDev& T, const float* src, unsigned long long id, int flag,
+                                            int b0, int n_rows, float* __restrict__ out, int io_stride, int off,
+                                            int off2, int split, int lane, unsigned char* wbuf, int use_bulk) {
+    if (split < T.dim) {       // split-row feature (plan creation guarantees vec4 rows that fit the buffer)
+        pull_rows_split(T, src, id, flag, b0, n_rows, out, io_stride, off, off2, split, lane, wbuf);
+        return;
+    }
+    if (use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
+        pull_rows_bulk(T, src, id, flag, b0, n_rows, out, io_stride, off, lane, wbuf);
+        return;
+    }
+    switch (T.lpr) {
+        case 1: pull_rows<1>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+        case 2: pull_rows<2>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+        case 4: pull_rows<4>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+        case 8: pull_rows<8>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+        case 16: pull_rows<16>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+        default: pull_rows<32>(T, src, id, flag, b0, n_rows, out, io_stride, off, lane); break;
+    }
+}
+
+// where does the row of lookup (f, b) live? flag: 0 invalid id / padding, 1 row at *src, 2 initializer value
+__device__ __forceinline__ int pull_resolve(const TableDev& T, const PlanDev& P, unsigned long long id,
+                                            const float** srcp) {
+    const int W = P.W;
+    const float* src = nullptr;
+    int flag = 0;
+    {
+        if (!T.is_hash) {
+            if (id < T.vocab) {
+                int o = owner_of(T, id, W);
+                src = T.w[o] + local_row_of(T, id) * (unsigned long long)T.wstride;
+                flag = 1;
+            }
+        } else if ((id >> 63) == 0) {
+            int o = owner_of(T, id, W);
+            const unsigned long long* keys = T.keys[o];
+            unsigned long long mask = T.rows - 1, h = exb_hash64(id) & mask;
+            flag = 2;
+            for (unsigned long long probe = 0; probe <= mask; ++probe) {
+                unsigned long long k = keys[h];
+                if (k == id) {
+                    src = T.w[o] + h * (unsigned long long)T.wstride;
+                    flag = 1;
+                    break;
+                }
+                if (k == EXB_EMPTY_KEY) break;
+                h = (h + 1) & mask;
+            }
+        }
+    }
+    *srcp = src;
+    return flag;
+}
+
 // one warp task of the pull: the 32 lookups (f, b0 .. b0+31)
 __device__ __forceinline__ void pull_one_task(const SmemView& S, const PlanDev& P, const long long* __restrict__ ids,
                                               float* __restrict__ out, int n_rows, int task, int lane,
@@ -218,21 +281,17 @@ __device__ __forceinline__ void pull_one_task(const SmemView& S, const PlanDev& 
         }
     }
     const int off = S.feat_off[f];
-    if (P.use_bulk && T.vec4 && T.wstride * 4 <= EXB_PULL_WARP_BUF) {
-        pull_rows_bulk(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane, wbuf);
+    int bulk;
+    if (P.use_bulk && pull_fast_geometry(T, S.feat_split[f], &bulk)) {     // one pass: the benchmark's row shapes
+        pull_rows_fast(T, src, id, flag, b0, n_rows, out, P.io_stride, off, S.feat_off2[f], S.feat_split[f], bulk, lane,
+                       wbuf, [] {});
         return;
     }
-    switch (T.lpr) {
-        case 1: pull_rows<1>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        case 2: pull_rows<2>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        case 4: pull_rows<4>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        case 8: pull_rows<8>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        case 16: pull_rows<16>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-        default: pull_rows<32>(T, src, id, flag, b0, n_rows, out, P.io_stride, off, lane); break;
-    }
+    pull_rows_slow(T, src, id, flag, b0, n_rows, out, P.io_stride, off, S.feat_off2[f], S.feat_split[f], lane, wbuf,
+                   P.use_bulk);
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long* __restrict__ ids,
                 float* __restrict__ out, int n_rows) {
     extern __shared__ __align__(16) unsigned char exb_smem[];
@@ -334,8 +393,8 @@ __device__ __forceinline__ void move_rows(const TableDev& T, const float* src, f
     }
 }
 
-__device__ __forceinline__ void move_rows_dispatch(const TableDev& T, const float* src, float* dst,
-                                                   int mode, int lane) {
+__device__ __noinline__ void move_rows_dispatch(const TableDev& T, const float* src, float* dst,
+                                               int mode, int lane) {
     switch (T.lpr) {
         case 1: move_rows<1>(T, src, dst, mode, lane); break;
         case 2: move_rows<2>(T, src, dst, mode, lane); break;
@@ -345,6 +404,15 @@ __device__ __forceinline__ void move_rows_dispatch(const TableDev& T, const floa
         default: move_rows<32>(T, src, dst, mode, lane); break;
     }
 }
+
+// non-bulk optimizer path (rows that do not fit the warp buffer, dim < 4): out of line, see pull_rows_slow
+template <int LPR>
+__device__ __forceinline__ void apply_rows(const TableDev& T, const PlanDev& P, float* accbase,
+                                           unsigned long long key, unsigned long long row, unsigned h,
+                                           unsigned cnt, int flag, int lane);
+__device__ __noinline__ void apply_rows_slow(const TableDev& T, const PlanDev& P, float* accbase,
+                                             unsigned long long key, unsigned long long row, unsigned h,
+                                             unsigned cnt, int flag, int lane);
 
 // block-wide exclusive prefix of ceil(cnt/32) over n (<= EXB_MAX_SEG) segments -> s_prefix[0..n]
 __device__ __forceinline__ void block_task_prefix(const unsigned* cnt, int n, int* s_prefix,
@@ -544,6 +612,19 @@ __device__ __forceinline__ void apply_rows(const TableDev& T, const PlanDev& P, 
     }
 }
 
+__device__ __noinline__ void apply_rows_slow(const TableDev& T, const PlanDev& P, float* accbase,
+                                             unsigned long long key, unsigned long long row, unsigned h,
+                                             unsigned cnt, int flag, int lane) {
+    switch (T.lpr) {
+        case 1: apply_rows<1>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        case 2: apply_rows<2>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        case 4: apply_rows<4>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        case 8: apply_rows<8>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        case 16: apply_rows<16>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+        default: apply_rows<32>(T, P, accbase, key, row, h, cnt, flag, lane); break;
+    }
+}
+
 __global__ void __launch_bounds__(256, 2)
 exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                        const long long* __restrict__ ids, const float* __restrict__ grads,
@@ -731,14 +812,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             if (trt && lane == 0) { __threadfence(); trt[6] = globaltimer_ns(); }
             continue;
         }
-        switch (T.lpr) {
-            case 1: apply_rows<1>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 2: apply_rows<2>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 4: apply_rows<4>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 8: apply_rows<8>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 16: apply_rows<16>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            default: apply_rows<32>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-        }
+        apply_rows_slow(T, P, accbase, key, row, h, cnt, flag, lane);
     }
     n_unique_local = __reduce_add_sync(0xffffffffu, n_unique_local);
     if (lane == 0 && n_unique_local) atomicAdd(&P.stats[2], (unsigned long long)n_unique_local);

@@ -126,28 +126,60 @@ exb_plan_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
 // Training pull: the stateless one-pass gather of exb_pull_kernel (every lookup reads its row where it lives --
 // measured on 2 and 8 B200s the step is bound by the NUMBER of dependent phases, not by NVLink bytes, so the
 // one-pass gather beats the unique-row pull of exb_pull2_kernel) with the batch's de-duplication plan built IN
-// THE SAME LAUNCH: 6 warps of every CTA gather, 2 warps insert ids. Both roles are latency bound and interleave
-// on the SM's schedulers; the plan costs no launch, no stream fork and leaves the critical path.
-#define EXB_PP_GATHER_WARPS 6
-__global__ void __launch_bounds__(256, 3)
+// THE SAME LAUNCH and in the shadow of the gather: every warp issues the cp.async loads of its 32 rows, inserts
+// the same 32 ids into the slot's map while the rows are in flight, then waits and writes the rows out. The
+// plan costs no launch, no stream fork, no second read of the ids and (nearly) no time.
+__global__ void __launch_bounds__(256, 2)
 exb_pull_plan_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long* __restrict__ ids,
                      float* __restrict__ out, int n_rows, int which) {
     extern __shared__ __align__(16) unsigned char exb_smem[];
+    // in-kernel phase clock of warp 0 of the LAST CTA (stats[16..23], "probe" in CudaEngine.status())
+#define PP_STAMP(i) do { if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) P.stats[16 + (i)] = globaltimer_ns(); } while (0)
+    PP_STAMP(0);
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
+    PP_STAMP(1);
     pdl_wait();
+    PP_STAMP(2);
     const SlotDev L = pick_slot(P, which);
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     if (P.W > 1) peer_wait(P);
-    if (wic < EXB_PP_GATHER_WARPS) {
-        unsigned char* wbuf = exb_smem + exb_smem_bytes(P.PT, P.F, false) + (size_t)wic * EXB_PULL_WARP_BUF;
-        const int gw = blockIdx.x * EXB_PP_GATHER_WARPS + wic, ngw = gridDim.x * EXB_PP_GATHER_WARPS;
-        for (int task = gw; task < P.num_tasks; task += ngw) pull_one_task(S, P, ids, out, n_rows, task, lane, wbuf);
-    } else {
-        constexpr int PW = 8 - EXB_PP_GATHER_WARPS;
-        const int pw = blockIdx.x * PW + (wic - EXB_PP_GATHER_WARPS), npw = gridDim.x * PW;
-        for (int task = pw; task < P.num_tasks; task += npw) plan_one_task(S, P, L, ids, n_rows, task, lane);
+    PP_STAMP(3);
+    unsigned char* wbuf = exb_smem + exb_smem_bytes(P.PT, P.F, false) + (size_t)wic * EXB_PULL_WARP_BUF;
+    for (int task = warp; task < P.num_tasks; task += nwarps) {
+        const int f = find_segment(S.task_prefix, P.F, task);
+        const int b0 = (task - S.task_prefix[f]) * 32;
+        if (b0 >= n_rows) continue;
+        const int pt = S.feat_pt[f];
+        const TableDev& T = S.tab[pt];
+        const int b = b0 + lane;
+        int bulk;
+        if (!(P.use_bulk && pull_fast_geometry(T, S.feat_split[f], &bulk))) {   // odd row shapes: plan, then gather
+            plan_one_task(S, P, L, ids, n_rows, task, lane);
+            pull_one_task(S, P, ids, out, n_rows, task, lane, wbuf);
+            continue;
+        }
+        unsigned long long id = 0;
+        const float* src = nullptr;
+        int flag = 0;
+        if (b < n_rows) {
+            id = (unsigned long long)__ldg(ids + (size_t)b * P.ncols + S.feat_col[f]);
+            flag = pull_resolve(T, P, id, &src);
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) P.stats[20] = globaltimer_after(id + (unsigned long long)src);
+        pull_rows_fast(T, src, id, flag, b0, n_rows, out, P.io_stride, S.feat_off[f], S.feat_off2[f], S.feat_split[f],
+                       bulk, lane, wbuf, [&] {
+            PP_STAMP(5);
+            const unsigned h = slot_insert_warp(P, L, S, pt, id, flag != 0, lane, L.ulist, L.ukeys, L.ucount);
+            if (h != 0xFFFFFFFFu) atomicAdd(&L.cmap_cnt[S.map_off[pt] + h], 1u);
+            if (b < n_rows) L.slot_of[(size_t)f * P.B + b] = h;
+            if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) P.stats[22] = globaltimer_after(h);
+        });
     }
+    PP_STAMP(7);
+#undef PP_STAMP
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         atomicAdd(&P.stats[0], (unsigned long long)n_rows * (unsigned long long)P.F);
         atomicAdd(&P.stats[3], 1ull);
@@ -252,6 +284,63 @@ __device__ __forceinline__ void zero_rows(const TableDev& T, float* dst, int on,
         const int m = __shfl_sync(0xffffffffu, on, r);
         if (!m) continue;
         for (int c = gl * 4; c < wstride; c += lpr * 4) *reinterpret_cast<float4*>(d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// gradient rows of a split-row feature (see pull_rows_split) are gathered from two places of the gradient row
+// and added into the accumulator row: columns [0, split) from src, [split, dim) from src2, pad columns 0
+template <int LPR>
+__device__ __forceinline__ void accum_rows_split_t(const TableDev& T, const float* src, const float* src2, int split,
+                                                   float* dst, int mode, int lane) {
+    const int wstride = T.wstride, dim = T.dim;
+    constexpr int RP = 32 / LPR;
+    constexpr int U = LPR >= 8 ? 8 : LPR;              // rows in flight per lane group
+    const int gl = lane % LPR, sub = lane / LPR;
+    for (int cb = 0; cb < wstride; cb += LPR * 4) {    // one iteration unless the row is wider than 128 floats
+        const int c = cb + gl * 4;
+        const bool cin = c < wstride;
+#pragma unroll 1
+        for (int p0 = 0; p0 < LPR; p0 += U) {
+            float4 v[U];
+            float* d[U];
+            int m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = (p0 + u) * RP + sub;
+                const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+                const float* s2 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src2, r);
+                d[u] = (float*)__shfl_sync(0xffffffffu, (unsigned long long)dst, r);
+                m[u] = __shfl_sync(0xffffffffu, mode, r);
+                if (!cin) m[u] = 0;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m[u]) {
+                    if (c + 4 <= split) v[u] = ld_stream_v4(s + c);
+                    else {
+                        float t[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = c + e;
+                            t[e] = col < split ? s[col] : (col < dim ? s2[col - split] : 0.f);
+                        }
+                        v[u] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (m[u]) red_add_v4(d[u] + c, v[u]);
+        }
+    }
+}
+__device__ __noinline__ void accum_rows_split(const TableDev& T, const float* src, const float* src2, int split,
+                                              float* dst, int mode, int lane) {
+    switch (T.lpr) {
+        case 1: accum_rows_split_t<1>(T, src, src2, split, dst, mode, lane); break;
+        case 2: accum_rows_split_t<2>(T, src, src2, split, dst, mode, lane); break;
+        case 4: accum_rows_split_t<4>(T, src, src2, split, dst, mode, lane); break;
+        case 8: accum_rows_split_t<8>(T, src, src2, split, dst, mode, lane); break;
+        case 16: accum_rows_split_t<16>(T, src, src2, split, dst, mode, lane); break;
+        default: accum_rows_split_t<32>(T, src, src2, split, dst, mode, lane); break;
     }
 }
 
@@ -409,7 +498,10 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
         float* dst = nullptr;
         int mode = 0;
         if (h != 0xFFFFFFFFu) { dst = L.acc + S.acc_off[pt] + (unsigned long long)h * T.wstride; mode = 1; }
-        move_rows_dispatch(T, src, dst, mode, lane);
+        if (S.feat_split[f] < T.dim)
+            accum_rows_split(T, src, grads + (size_t)b * P.io_stride + S.feat_off2[f], S.feat_split[f], dst, mode, lane);
+        else
+            move_rows_dispatch(T, src, dst, mode, lane);
     }
     EXB_STAMP(1);
     unsigned n_sent = 0;
@@ -578,14 +670,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
             apply_rows_bulk(T, P, accbase, key, row, h, cnt, flag, lane, wbuf, wmeta, chunk, nullptr);
             continue;
         }
-        switch (T.lpr) {
-            case 1: apply_rows<1>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 2: apply_rows<2>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 4: apply_rows<4>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 8: apply_rows<8>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            case 16: apply_rows<16>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-            default: apply_rows<32>(T, P, accbase, key, row, h, cnt, flag, lane); break;
-        }
+        apply_rows_slow(T, P, accbase, key, row, h, cnt, flag, lane);
     }
     if (W > 1) {
         // map entries of the ids other ranks own (shipped in P2) are cleared here: no insert is in flight any more

@@ -57,7 +57,8 @@ class FusedEmbeddings(nn.Module):
     column (`col`), e.g. the dim-D and the dim-1 table of one sparse feature.
     """
 
-    def __init__(self, specs, batch, optimizer, num_shards=None, ncols=None, feat_offsets=None, io_stride=None):
+    def __init__(self, specs, batch, optimizer, num_shards=None, ncols=None, feat_offsets=None, io_stride=None,
+                 feat_offsets2=None, feat_split=None):
         super().__init__()
         ctx = get_context()
         self.ctx = ctx
@@ -74,7 +75,7 @@ class FusedEmbeddings(nn.Module):
             ctx.backend.ensure_allocated(self.metas)
             self.group = ctx.backend.engine.make_plan([m.handle for m in self.metas], batch, feat_offsets=feat_offsets,
                                                       io_stride=io_stride, feat_cols=[s["col"] for s in specs],
-                                                      ncols=ncols)
+                                                      ncols=ncols, feat_offsets2=feat_offsets2, feat_split=feat_split)
             ctx.backend.engine.connect(ctx.backend.group)
         else:
             self.group = ctx.backend.make_group(self.metas, batch, feat_cols=[s["col"] for s in specs], ncols=ncols)

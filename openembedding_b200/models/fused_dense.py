@@ -105,7 +105,7 @@ class FusedCTR:
 
     def __init__(self, vocab_sizes, num_dense=13, embedding_dim=64, model="deepfm", batch=4096, hidden=None,
                  sparse_optimizer=None, cache_threshold=0, lr=0.001, initial_accumulator_value=0.1, eps=1e-7,
-                 num_shards=None, dw_splits=8, seed=0):
+                 num_shards=None, dw_splits=8, seed=0, pack_linear=None):
         from .ctr import FusedEmbeddings
         ctx = get_context()
         if ctx.device.type != "cuda":
@@ -133,11 +133,25 @@ class FusedCTR:
         self.XS = _r(self.K0p + self.ns, 4)
         sparse_optimizer = sparse_optimizer or {"category": "adagrad"}
         zero = {"category": "constant", "value": 0.0}
-        specs = [{"vocab": self.vocab[f], "dim": embedding_dim, "col": f, "initializer": zero} for f in self.server]
-        specs += [{"vocab": self.vocab[f], "dim": 1, "col": f, "initializer": zero} for f in self.server]
-        offs = [j * Dp for j in range(self.ns)] + [self.lin0 + j for j in range(self.ns)]
-        self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards, ncols=nf,
-                                      feat_offsets=offs, io_stride=self.XS)
+        # pack_linear: the dim-D embedding and the dim-1 linear ("wide") weight of a sparse feature share ONE
+        # server row of dim D+1 (split-row feature): half the lookups, unique ids, hash inserts, NVLink rows and
+        # optimizer rows of the two-variables-per-feature layout of the reference benchmark
+        # (criteo_deepctr.py:60-110). Same math per element; the checkpoint then holds one variable per feature.
+        if pack_linear is None:
+            pack_linear = os.environ.get("EXB_PACK_LINEAR", "1") != "0" and os.environ.get("EXB_SPARSE_V2", "1") != "0"
+        self.pack_linear = bool(pack_linear)
+        if self.pack_linear:
+            specs = [{"vocab": self.vocab[f], "dim": embedding_dim + 1, "col": f, "initializer": zero} for f in self.server]
+            self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards, ncols=nf,
+                                          feat_offsets=[j * Dp for j in range(self.ns)], io_stride=self.XS,
+                                          feat_offsets2=[self.lin0 + j for j in range(self.ns)],
+                                          feat_split=[embedding_dim] * self.ns)
+        else:
+            specs = [{"vocab": self.vocab[f], "dim": embedding_dim, "col": f, "initializer": zero} for f in self.server]
+            specs += [{"vocab": self.vocab[f], "dim": 1, "col": f, "initializer": zero} for f in self.server]
+            offs = [j * Dp for j in range(self.ns)] + [self.lin0 + j for j in range(self.ns)]
+            self.sparse = FusedEmbeddings(specs, batch, sparse_optimizer, num_shards=num_shards, ncols=nf,
+                                          feat_offsets=offs, io_stride=self.XS)
         self.group = self.sparse.group
         dev = self.dev
         f32, bf16 = torch.float32, torch.bfloat16

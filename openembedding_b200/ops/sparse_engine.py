@@ -174,8 +174,9 @@ class CudaEngine:
                 plan.connected = True
 
     # ---------------------------------------------------------------- plans
-    def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None):
-        return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols, ncols)
+    def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None,
+                  feat_offsets2=None, feat_split=None):
+        return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols, ncols, feat_offsets2, feat_split)
 
     # --------------------------------------------------------------- status
     def status(self):
@@ -287,7 +288,11 @@ class CudaEngine:
 class SparsePlan:
     """Fused lookup/update over F features of one batch (ids ``[B, F]`` int64)."""
 
-    def __init__(self, engine, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None):
+    def __init__(self, engine, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None,
+                 feat_offsets2=None, feat_split=None):
+        """``feat_split`` / ``feat_offsets2``: SPLIT-ROW features -- columns ``[0, split)`` of a feature's table row are
+        read / written at ``feat_offsets[f]`` of the activation row and columns ``[split, dim)`` at
+        ``feat_offsets2[f]`` (one table row, e.g. [embedding | linear weight], feeding two places of the model)."""
         self.e = engine
         self.lib = engine.lib
         self.F = len(feat_tables)
@@ -302,6 +307,9 @@ class SparsePlan:
                 feat_offsets.append(o)
                 o += w
             total = (o + 3) // 4 * 4
+        elif feat_split is not None:
+            total = max([o + min(w, sp) for o, w, sp in zip(feat_offsets, widths, feat_split)] +
+                        [o2 + d - sp for o2, d, sp in zip(feat_offsets2, self.dims, feat_split) if sp < d])
         else:
             total = max(o + w for o, w in zip(feat_offsets, widths))
         self.feat_offsets = [int(o) for o in feat_offsets]
@@ -311,7 +319,16 @@ class SparsePlan:
         ft = (ctypes.c_int32 * self.F)(*self.feat_tables)
         fo = (ctypes.c_int32 * self.F)(*self.feat_offsets)
         fc = (ctypes.c_int32 * self.F)(*self.feat_cols)
-        self.h = self.lib.exb_plan_create(engine.h, self.F, ft, fo, fc, self.ncols, self.B, self.io_stride)
+        self.feat_split = [int(x) for x in feat_split] if feat_split is not None else None
+        self.feat_offsets2 = [int(x) for x in feat_offsets2] if feat_offsets2 is not None else None
+        if self.feat_split is not None:
+            if os.environ.get("EXB_SPARSE_V2", "1") == "0":
+                raise RuntimeError("split-row features need the v2 sparse kernels (EXB_SPARSE_V2=1)")
+            fo2 = (ctypes.c_int32 * self.F)(*self.feat_offsets2)
+            fsp = (ctypes.c_int32 * self.F)(*self.feat_split)
+            self.h = self.lib.exb_plan_create2(engine.h, self.F, ft, fo, fc, self.ncols, self.B, self.io_stride, fo2, fsp)
+        else:
+            self.h = self.lib.exb_plan_create(engine.h, self.F, ft, fo, fc, self.ncols, self.B, self.io_stride)
         if not self.h:
             raise RuntimeError("exb_plan_create: " + self.lib.exb_cuda_last_error().decode())
         self.connected = engine.world == 1
@@ -321,7 +338,7 @@ class SparsePlan:
         # EXB_PULL2=1: training pulls of world > 1 move UNIQUE remote rows (exb_pull2_kernel: gather unique rows,
         # grid barrier, expand). Measured slower than the one-pass gather on 2 and 8 B200s (the step is bound by the
         # number of dependent phases, not by NVLink bytes -- profiles/r2/sparse_v2.md), hence off by default.
-        self.pull2 = os.environ.get("EXB_PULL2", "0") == "1"
+        self.pull2 = os.environ.get("EXB_PULL2", "0") == "1" and self.feat_split is None
         self._armed = [None, None]       # relative slots (0 current, 1 next): ((ids ptr, n), origin) or None
         engine.plans.append(self)
         if engine.world == 1:
@@ -431,6 +448,8 @@ class SparsePlan:
         return self._trace
 
     def feature_slices(self):
+        if self.feat_split is not None:
+            return [slice(o, o + min(d, sp)) for o, d, sp in zip(self.feat_offsets, self.dims, self.feat_split)]
         return [slice(o, o + d) for o, d in zip(self.feat_offsets, self.dims)]
 
     def close(self):

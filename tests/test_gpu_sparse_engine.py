@@ -255,3 +255,71 @@ def test_checkpoint_row_access_and_rehash():
     w3, s3 = e.gather_rows(t, keys)
     assert torch.equal(w, w3) and torch.equal(s, s3)
     e.close()
+
+
+@pytest.mark.parametrize("world,dim", [(1, 10), (1, 65), (2, 65), (2, 17)])
+def test_split_row_feature(world, dim):
+    """one table row [embedding(D) | linear(1)] feeding two places of the activation / gradient row"""
+    from openembedding_b200.ops.sparse_engine import CudaEngine
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    D = dim - 1
+    Dp = (D + 3) // 4 * 4
+    io = Dp * 2 + 8                      # two features' embedding blocks, then the linear columns
+    lin0 = Dp * 2 + 1
+    engines = [CudaEngine(0, r, world, max_ctas=6) for r in range(world)]
+    for e in engines:
+        for vid in range(2):
+            t = e.add_table(dim, 5000, vid == 1, capacity=1 << 12)
+            e.set_initializer(t, UNIFORM, vid)
+            e.set_optimizer(t, ADAGRAD)
+            e.alloc(t)
+    plans = [e.make_plan([0, 1], 160, feat_offsets=[0, Dp], io_stride=io, feat_offsets2=[lin0, lin0 + 1],
+                         feat_split=[D, D]) for e in engines]
+    if world > 1:
+        CudaEngine.connect_local(engines)
+    oracles = [_oracle(dim, 5000, vid == 1, UNIFORM, ADAGRAD, vid) for vid in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    worst = 0.0
+    for step in range(3):
+        ids = [torch.stack([torch.randint(0, 300, (160,)), torch.randint(0, 300, (160,)) * 1000003 + 7], 1).contiguous().to(dev)
+               for _ in range(world)]
+        grads = [torch.randn(160, io, device=dev) for _ in range(world)]
+        outs = []
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                outs.append(plans[r].pull(ids[r], train=True))
+        torch.cuda.synchronize()
+        for r in range(world):
+            for f in range(2):
+                lib, h = oracles[f]
+                want = _oracle_pull(lib, h, ids[r][:, f].cpu().numpy(), dim)
+                got = torch.cat([outs[r][:, f * Dp:f * Dp + D], outs[r][:, lin0 + f:lin0 + f + 1]], 1).cpu().numpy()
+                worst = max(worst, float(np.abs(want - got).max()))
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                plans[r].push_update(ids[r], grads[r])
+        torch.cuda.synchronize()
+        for e in engines:
+            e.check()
+        for f in range(2):
+            lib, h = oracles[f]
+            for r in range(world):
+                k = np.ascontiguousarray(ids[r][:, f].cpu().numpy(), dtype=np.uint64)
+                g = torch.cat([grads[r][:, f * Dp:f * Dp + D], grads[r][:, lin0 + f:lin0 + f + 1]], 1)
+                g = np.ascontiguousarray(g.cpu().numpy(), dtype=np.float32)
+                lib.exb_var_push(h, k.ctypes.data, k.size, g.ctypes.data, None)
+            lib.exb_var_update(h)
+    probe = torch.stack([torch.arange(160) % 300, (torch.arange(160) % 300) * 1000003 + 7], 1).contiguous().to(dev)
+    out = plans[0].pull(probe)
+    for f in range(2):
+        lib, h = oracles[f]
+        want = _oracle_pull(lib, h, probe[:, f].cpu().numpy(), dim)
+        got = torch.cat([out[:, f * Dp:f * Dp + D], out[:, lin0 + f:lin0 + f + 1]], 1).cpu().numpy()
+        worst = max(worst, float(np.abs(want - got).max()))
+    for lib, h in oracles:
+        lib.exb_var_destroy(h)
+    for e in engines:
+        e.close()
+    assert worst < 5e-4, worst

@@ -9,5 +9,6 @@ b() { name=$1; shift
  grep '^{' gpurun_out/r2_bench_$name.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['push_update_phases_us'])"
 }
 EXTRA="" b ours_v2 EXB_SPARSE_V2=1
-EXTRA="--prefetch" b ours_v2pf EXB_SPARSE_V2=1
+EXTRA="" b ours_v2_nopack EXB_SPARSE_V2=1 EXB_PACK_LINEAR=0
 EXTRA="" b ours_v1 EXB_SPARSE_V2=0
+EXB_SPARSE_V2=1 timeout 300 python tools/mp_timeline.py --steps 40 2>&1 | grep -E "^rank 0|phases"
