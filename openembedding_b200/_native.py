@@ -133,6 +133,18 @@ def cuda():
         P(lib, "exb_pull_plan", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_int, c_uint64])
         P(lib, "exb_plan_memory", c_int, [c_void_p, u64p])
         P(lib, "exb_engine_status_ptr", c_uint64, [c_void_p])
+        P(lib, "exb_tier_create", c_void_p, [c_void_p, c_int, c_uint64])
+        P(lib, "exb_tier_destroy", None, [c_void_p])
+        P(lib, "exb_tier_admit", c_int, [c_void_p, c_uint64, c_uint64, c_uint32, c_uint64])
+        P(lib, "exb_tier_flush", c_int, [c_void_p, c_uint32, c_uint64])
+        P(lib, "exb_tier_evict", c_int, [c_void_p, c_uint64, c_uint32, c_uint64])
+        P(lib, "exb_tier_clear", c_int, [c_void_p, c_int])
+        P(lib, "exb_tier_stats", c_int, [c_void_p, u64p])
+        P(lib, "exb_tier_info", c_int, [c_void_p, u64p])
+        P(lib, "exb_tier_host_enumerate", c_int, [c_void_p, c_uint64, c_uint64, u64p])
+        P(lib, "exb_tier_hkeys_ptr", c_uint64, [c_void_p])
+        P(lib, "exb_tier_host_put", c_int, [c_void_p, c_void_p, c_uint64, c_void_p])
+        P(lib, "exb_tier_relayout", c_int, [c_void_p])
         _cuda = lib
     return _cuda
 

@@ -118,7 +118,7 @@ class Variable:
     """
 
     def __init__(self, initializer=None, trainable=None, name=None, dtype=None, shape=None, num_shards=None,
-                 sparse_as_dense=False, graph_var=None, host_tier_rows=None):
+                 sparse_as_dense=False, graph_var=None, host_tier_rows=None, host_store_rows=None):
         if not num_shards:
             num_shards = -1
         if shape is not None:
@@ -171,7 +171,7 @@ class Variable:
         self.tier = None
         if tiered:
             from .host_tier import make_tiered
-            self.tier = make_tiered(ctx, self.variable, host_tier_rows)
+            self.tier = make_tiered(ctx, self.variable, host_tier_rows, host_rows=host_store_rows)
         self.model_uuid = ctx.model_uuid
         self.optimizer_set = False
         self._prefetched = []
@@ -289,7 +289,8 @@ class Embedding(nn.Module):
 
     def __init__(self, input_dim, output_dim, embeddings_initializer="uniform", embeddings_regularizer=None,
                  activity_regularizer=None, embeddings_constraint=None, mask_zero=False, input_length=None,
-                 num_shards=None, sparse_as_dense=False, explicit=True, dtype=None, name=None, host_tier_rows=None):
+                 num_shards=None, sparse_as_dense=False, explicit=True, dtype=None, name=None, host_tier_rows=None,
+                 host_store_rows=None):
         super().__init__()
         if input_dim is None:
             input_dim = -1
@@ -324,7 +325,8 @@ class Embedding(nn.Module):
             self.embeddings = nn.Parameter(torch.zeros((1, self.output_dim), dtype=dtype, device=ctx.device))
             self.variable = Variable(initializer=dict(self.server_initializer), dtype=dtype,
                                      shape=(self.input_dim, self.output_dim), num_shards=num_shards,
-                                     graph_var=self.embeddings, host_tier_rows=host_tier_rows)
+                                     graph_var=self.embeddings, host_tier_rows=host_tier_rows,
+                                     host_store_rows=host_store_rows)
         self.built = True
 
     def forward(self, inputs, offsets=None, per_sample_weights=None, mode="sum"):

@@ -289,6 +289,11 @@ class CudaBackend:
         self.engine.set_optimizer(meta.handle, cfg)
         if getattr(meta, "allocated", False):
             self.engine.commit()
+        if getattr(meta, "tiered", False):
+            from .host_tier import tier_of
+            t = tier_of(meta)
+            if t is not None and hasattr(t, "on_optimizer_change"):
+                t.on_optimizer_change()
 
     def ensure_allocated(self, metas=None):
         """Collective: materialise not-yet-allocated tables and map them on every peer."""
@@ -440,8 +445,8 @@ class CudaBackend:
         import torch.distributed as dist
         grew = False
         for meta in self.vars:
-            if not (meta.is_hash and meta.allocated):
-                continue
+            if not (meta.is_hash and meta.allocated) or getattr(meta, "tiered", False):
+                continue          # a tiered table's HBM shard is a fixed-size cache: it evicts, it does not grow
             size = self.engine.table_size(meta.handle)
             cap = self.engine.table_info(meta.handle)["rows"]
             last = getattr(meta, "_last_size", 0)

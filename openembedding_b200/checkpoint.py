@@ -95,16 +95,28 @@ def _save_model_local(ctx, path, include_optimizer=True, num_files=None, persist
             w = writers[file_id]
             itemsize = 4 if meta.dtype == "float32" else 8
             sls = be.state_dim(meta) * itemsize if include_optimizer else 0
-            n_items = 0 if persist is not None else be.num_items(meta)
-            cfg = dump_variable_config(be.table_kind(meta), n_items if persist is None else be.num_items(meta),
+            # host-tier variables: the host store is authoritative once the dirty cache rows are written back
+            # (the reference's PMem tables dump every row through the normal path too)
+            from .host_tier import GpuTieredVariable, tier_of
+            tier = tier_of(meta)
+            gpu_tier = tier if isinstance(tier, GpuTieredVariable) else None
+            if tier is not None and persist is None:
+                tier.flush()
+            if gpu_tier is not None:
+                n_items = 0 if persist is not None else gpu_tier.num_items()
+            else:
+                n_items = 0 if persist is not None else (be.num_items(meta) if tier is None else tier.num_items())
+            cfg = dump_variable_config(be.table_kind(meta), n_items if persist is None else (be.num_items(meta) if tier is None else tier.num_items()),
                                        meta.optimizer, meta.initializer,
                                        include_optimizer=include_optimizer, extra=persist).encode()
             lib.exb_fw_header(w, vid, DTYPES[meta.dtype], meta.dim, meta.vocab, cfg, len(cfg),
                               shard_id, meta.shard_num, sls, n_items)
             if n_items:
                 written = 0
-                for idx, wts, sts in be.iter_local_rows(meta, block_rows(meta.dim, itemsize, sls),
-                                                        with_state=include_optimizer):
+                rows_iter = (tier.iter_rows(block_rows(meta.dim, itemsize, sls), with_state=include_optimizer)
+                             if tier is not None else
+                             be.iter_local_rows(meta, block_rows(meta.dim, itemsize, sls), with_state=include_optimizer))
+                for idx, wts, sts in rows_iter:
                     idx = np.ascontiguousarray(idx, dtype=np.uint64)
                     wts = np.ascontiguousarray(wts)
                     sts = np.ascontiguousarray(sts)
@@ -180,8 +192,12 @@ def _load_model_local(ctx, path, restore_config_only=False):
         raise ValueError("model meta not match\n%s\n%s" % (json.dumps(meta["variables"], indent=4),
                                                            json.dumps(mine, indent=4)))
     be = ctx.backend
+    from .host_tier import tier_of
     for m in ctx.variables:
-        be.clear(m)
+        if tier_of(m) is not None:
+            tier_of(m).clear(host_too=True)      # cache AND host store: the checkpoint replaces both
+        else:
+            be.clear(m)
     for st in ctx.storages:
         sdir = os.path.join(path, str(st.storage_id))
         if not os.path.isdir(sdir):
@@ -202,7 +218,10 @@ def _load_model_local(ctx, path, restore_config_only=False):
                     continue
                 _, hdr, gid, w, s = rec
                 var = st.variables[hdr["variable_id"]]
-                be.load_rows(var, gid, w, s)
+                if tier_of(var) is not None:
+                    tier_of(var).put_rows(gid, w, s)     # rows land in the host store; the cache refills on demand
+                else:
+                    be.load_rows(var, gid, w, s)
     try:
         sign = meta.get("model_sign", "")
         ctx.loaded_model_sign = sign

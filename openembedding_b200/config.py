@@ -137,6 +137,26 @@ def optimizer_state_dim(config, dim):
     return slots * dim + scalars
 
 
+def OPTIMIZER_SLOTS(config):
+    """(per-element state slots, trailing per-row scalars) of an optimizer -- exb_math.h opt_num_slots/scalars"""
+    kind, _ = optimizer_params(config)
+    return {0: 0, 1: 2, 2: 1, 3: 2, 4: 2, 5: 2, 6: 2, 7: 1, 8: 0}[kind], {3: 2, 4: 1, 8: 2}.get(kind, 0)
+
+
+def optimizer_slot_inits(config):
+    """initial values ([per slot], [per scalar]) of a fresh optimizer state -- exb_math.h opt_slot_init/opt_scalar_init"""
+    kind, p = optimizer_params(config)
+    nslots, nsc = OPTIMIZER_SLOTS(config)
+    slots = [float(p[1]) if (kind in (2, 5) and s == 0) else 0.0 for s in range(nslots)]
+    if kind in (3, 4):
+        scal = [1.0] * nsc
+    elif kind == 8:
+        scal = [float(p[2]), 0.0][:nsc]
+    else:
+        scal = [0.0] * nsc
+    return slots, scal
+
+
 _INIT_ALIASES = {
     # keras string identifiers used by tf.keras.layers.Embedding (exb.py:25-63)
     "uniform": {"category": "uniform", "minval": -0.05, "maxval": 0.05},

@@ -134,6 +134,11 @@ class Context:
             self.monitor = None
         if getattr(self, "backend", None) is not None:
             try:
+                from . import host_tier
+                host_tier.close_all()          # tiers hold engine handles: before the backend goes away
+            except Exception:
+                pass
+            try:
                 self.backend.close()
             except Exception:
                 pass

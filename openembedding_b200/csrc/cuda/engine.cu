@@ -883,3 +883,5 @@ int exb_plan_memory(void* ph, uint64_t* out) {
 uint64_t exb_engine_status_ptr(void* h) { return (uint64_t)(((Engine*)h)->sync_local + OFF_STATUS); }
 
 }  // extern "C"
+
+#include "host_tier.cuh"
