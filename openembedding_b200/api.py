@@ -338,6 +338,13 @@ class Embedding(nn.Module):
         ``nn.EmbeddingBag``) and get one pooled row per bag (``mode`` sum | mean | max is
         applied on this rank after ONE pull of the flat ids, so duplicated ids inside a batch
         travel once). A ``torch.nested`` tensor is accepted too and returns a nested result."""
+        grp = getattr(self, "_group", None)
+        if grp is not None and offsets is None and not getattr(inputs, "is_nested", False):
+            hit = grp.lookup(self, inputs)
+            if hit is not None:
+                if self.activity_regularizer is not None and self.training:
+                    self.activity_loss = self.activity_regularizer(hit)
+                return hit
         if offsets is None and getattr(inputs, "is_nested", False):
             parts = inputs.unbind()
             flat = torch.cat([p.reshape(-1) for p in parts])
@@ -452,6 +459,8 @@ def _DistributedOptimizer(T):
                             tracked.append(v)
                         stash.append((p, p.grad))
                         p.grad = None          # the dummy [1, dim] parameter is never updated locally
+            for grp in getattr(ctx, "groups", []):
+                grp.flush()                                # ONE push+update launch for every grouped Embedding
             if tracked:
                 ctx.backend.update([v.variable for v in tracked])
                 for v in tracked:
@@ -520,7 +529,20 @@ def _to_original(model):
     memo = {}
     for _, layer in _iter_embeddings(model):   # do not deep-copy engine handles
         memo[id(layer)] = layer
+    grp = getattr(model, "_embedding_group", None)
+    if grp is not None:
+        memo[id(grp)] = grp
     clone = copy.deepcopy(model, memo)
+    if grp is not None:                        # the export is a plain model: no fused-group hooks, no engine state
+        for hooks in (clone._forward_pre_hooks, clone._forward_hooks):
+            for k in [k for k, h in hooks.items() if getattr(h, "__self__", None) is grp]:
+                del hooks[k]
+        for d in (getattr(clone, "_forward_pre_hooks_with_kwargs", None), getattr(clone, "_forward_hooks_with_kwargs", None)):
+            if isinstance(d, dict):
+                for k in [k for k in d if k not in clone._forward_pre_hooks and k not in clone._forward_hooks]:
+                    del d[k]
+        if "_embedding_group" in clone.__dict__:
+            del clone.__dict__["_embedding_group"]
 
     def convert(parent):
         for cname, child in list(parent.named_children()):
@@ -678,6 +700,167 @@ class ModelCheckpoint:
             self.model.save(path, include_optimizer=self.include_optimizer)
 
 
+class _GroupPull(torch.autograd.Function):
+    """ONE pull launch for every server Embedding of a model; the gradient rows are kept for ONE fused
+    push+update at ``optimizer.step()`` (reference: 26 PullWeights + 26 PushGradients ops per step,
+    exb_ops.cpp:208-414)."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, group):
+        ctx.group = group
+        ctx.ids = ids
+        return group.plan.pull(ids, train=torch.is_grad_enabled())
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = ctx.group
+        g.pending = (ctx.ids, grad.contiguous())
+        return torch.zeros_like(g.anchor), None, None
+
+
+class EmbeddingGroup:
+    """Fused sparse path behind the public API (``distributed_model``).
+
+    All server-side ``Embedding`` layers of a model whose indices are fed DIRECTLY by a model input -- a whole
+    1-D / ``[B, 1]`` input tensor (positional, keyword or dict entry) or one column of a 2-D integer input, the
+    same condition as the reference's ``pulling`` (exb.py:645-691: "Embedding fed directly by exactly one
+    InputLayer") -- are served by ONE ``SparsePlan``: a forward pre-hook pulls all of them in one launch, every
+    layer's ``forward`` returns its slice, and ``distributed_optimizer.step()`` applies all their gradients in one
+    push+update launch. The mapping input -> layer is discovered by tracing the first forward pass; layers that do
+    not qualify (derived indices, multi-hot bags, host-tier tables, ``sparse_as_dense``) keep the per-variable path."""
+
+    def __init__(self, model):
+        self.model = model
+        self.ctx = get_context()
+        self.layers = [l for _, l in _iter_embeddings(model)
+                       if not l.sparse_as_dense and getattr(l.variable, "tier", None) is None]
+        for l in self.layers:
+            l._group = self
+        self.state = "trace" if (self.layers and self.ctx.device.type == "cuda") else "off"
+        self.trace = []             # (layer, indices tensor) seen during the traced forward
+        self.members = []           # [(layer, source)] source = (kind, key, column)
+        self.plan = None
+        self.cache = {}
+        self.pending = None
+        self.anchor = None
+        self.batch = None
+        self.ctx.groups = getattr(self.ctx, "groups", [])
+        self.ctx.groups.append(self)
+        model.register_forward_pre_hook(self._pre, with_kwargs=True)
+        model.register_forward_hook(self._post, with_kwargs=True)
+
+    # ---- inputs
+    @staticmethod
+    def _flatten_inputs(args, kwargs):
+        out = []
+        for i, a in enumerate(args):
+            if isinstance(a, dict):
+                out += [(("argdict", i, k), v) for k, v in a.items() if torch.is_tensor(v)]
+            elif isinstance(a, (list, tuple)):
+                out += [(("argseq", i, j), v) for j, v in enumerate(a) if torch.is_tensor(v)]
+            elif torch.is_tensor(a):
+                out.append((("arg", i, None), a))
+        for k, v in kwargs.items():
+            if torch.is_tensor(v):
+                out.append((("kw", k, None), v))
+        return out
+
+    @staticmethod
+    def _match(ind, inputs):
+        """which model input (and column) is this indices tensor?"""
+        if ind.dtype not in (torch.int64, torch.int32) or ind.dim() not in (1, 2):
+            return None
+        if ind.dim() == 2 and ind.shape[1] != 1:
+            return None
+        n = ind.shape[0]
+        for key, t in inputs:
+            if t.dtype != ind.dtype or t.device != ind.device or t.shape[0] != n:
+                continue
+            if t.dim() == ind.dim() and t.shape == ind.shape and t.data_ptr() == ind.data_ptr() and t.stride() == ind.stride():
+                return key + (None,)
+            if t.dim() == 2 and t.untyped_storage().data_ptr() == ind.untyped_storage().data_ptr():
+                off = (ind.data_ptr() - t.data_ptr()) // t.element_size()
+                if 0 <= off < t.shape[1] and ind.stride(0) == t.stride(0) and t.stride(1) == 1:
+                    return key + (int(off),)
+        return None
+
+    def _fetch(self, args, kwargs, src):
+        kind, a, b, col = src
+        if kind == "arg":
+            t = args[a]
+        elif kind == "argdict":
+            t = args[a][b]
+        elif kind == "argseq":
+            t = args[a][b]
+        else:
+            t = kwargs[a]
+        return t if col is None else t[:, col]
+
+    # ---- hooks
+    def _pre(self, module, args, kwargs):
+        self.cache = {}
+        if self.state == "trace":
+            self.trace = []
+            self._inputs = self._flatten_inputs(args, kwargs)
+            return None
+        if self.state != "on" or not torch.is_grad_enabled() or not module.training:
+            return None
+        try:
+            cols = [self._fetch(args, kwargs, src).reshape(-1) for _, src in self.members]
+        except Exception:
+            return None
+        n = cols[0].shape[0]
+        if n != self.batch or any(c.shape[0] != n for c in cols):
+            return None                                   # odd batch (last one of an epoch): per-variable path
+        ids = torch.stack([c.to(device=self.ctx.device, dtype=torch.int64) for c in cols], dim=1).contiguous()
+        out = _GroupPull.apply(self.anchor, ids, self)
+        for (layer, _), sl in zip(self.members, self.plan.feature_slices()):
+            self.cache[id(layer)] = out[:, sl]
+        return None
+
+    def lookup(self, layer, inputs):
+        if self.state == "trace":
+            self.trace.append((layer, inputs))
+            return None
+        hit = self.cache.pop(id(layer), None)
+        if hit is None:
+            return None
+        return hit.reshape(tuple(inputs.shape) + (layer.output_dim,)).to(layer.variable._tdtype)
+
+    def _post(self, module, args, kwargs, output):
+        if self.state != "trace":
+            return None
+        members, seen = [], set()
+        for layer, ind in self.trace:
+            src = self._match(ind, self._inputs) if torch.is_tensor(ind) else None
+            if src is not None and id(layer) not in seen and layer.variable.graph_var.requires_grad:
+                members.append((layer, src))
+                seen.add(id(layer))
+        self.trace, self._inputs = [], None
+        if len(members) < 2:
+            self.state = "off"
+            return None
+        n = self._fetch(args, kwargs, members[0][1]).reshape(-1).shape[0]
+        be = self.ctx.backend
+        metas = [l.variable.variable for l, _ in members]
+        be.ensure_allocated(metas)
+        self.plan = be.engine.make_plan([m.handle for m in metas], n)
+        be.engine.connect(be.group)
+        self.members, self.batch = members, n
+        self.anchor = torch.zeros(1, device=self.ctx.device, requires_grad=True)
+        self.state = "on"
+        return None
+
+    # ---- called by the distributed optimizer
+    def flush(self):
+        if self.pending is None:
+            return False
+        ids, grad = self.pending
+        self.pending = None
+        self.plan.push_update(ids, grad)
+        return True
+
+
 def distributed_model(model, sparse_as_dense_size=64, num_shards=None, override_method=True, explicit=False):
     """Replace every ``nn.Embedding`` of `model` by a server-side ``Embedding``
     (``sparse_as_dense`` when ``num_embeddings <= sparse_as_dense_size``) and add
@@ -702,6 +885,8 @@ def distributed_model(model, sparse_as_dense_size=64, num_shards=None, override_
     model.to(ctx.device)
     if override_method:
         model.__class__ = _DistributedModel(model.__class__)
+    if os.environ.get("EXB_API_FUSED", "1") != "0":
+        model._embedding_group = EmbeddingGroup(model)      # one pull / one push+update launch per step
     return model
 
 

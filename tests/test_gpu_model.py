@@ -136,3 +136,61 @@ def test_hash_table_grows_automatically():
     finally:
         oe.flags.device, oe.flags.config = old_dev, old_cfg
         reset_context()
+
+
+class _WideModel(torch.nn.Module):
+    """reference-style network script (examples/criteo_deepctr_network.py): nn.Embedding per sparse column,
+    one [B, F] id matrix sliced by column inside forward, plus a keyword id tensor"""
+
+    def __init__(self, vocab, dim):
+        super().__init__()
+        self.embs = torch.nn.ModuleList([torch.nn.Embedding(v, dim) for v in vocab])
+        self.lin = torch.nn.ModuleList([torch.nn.Embedding(v, 1) for v in vocab])
+        self.extra = torch.nn.Embedding(777, dim)
+        self.mlp = torch.nn.Sequential(torch.nn.Linear(dim * (len(vocab) + 1), 32), torch.nn.ReLU(), torch.nn.Linear(32, 1))
+
+    def forward(self, ids, extra=None):
+        e = [m(ids[:, f]) for f, m in enumerate(self.embs)] + [self.extra(extra)]
+        l = sum(m(ids[:, f]).squeeze(-1) for f, m in enumerate(self.lin))
+        return self.mlp(torch.cat(e, dim=-1)).squeeze(-1) + l
+
+
+def test_api_fused_group_matches_per_variable(cuda_context, monkeypatch):
+    """distributed_model groups every server Embedding fed directly by a model input into ONE plan
+    (one pull + one push+update launch per step); results are identical to the per-variable path"""
+    import openembedding_b200.torch as embed
+    from openembedding_b200.context import get_context, reset_context
+    vocab = [5000, 300, 70000, 1200, 90]
+    B = 192
+    res = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("EXB_API_FUSED", fused)
+        reset_context()
+        ctx = get_context()
+        torch.manual_seed(0)
+        model = embed.distributed_model(_WideModel(vocab, 8), sparse_as_dense_size=100)
+        opt = embed.distributed_optimizer(torch.optim.Adagrad(model.parameters(), lr=0.05, initial_accumulator_value=0.1))
+        g = torch.Generator().manual_seed(3)
+        losses = []
+        for step in range(8):
+            ids = torch.stack([torch.randint(0, v, (B,), generator=g) for v in vocab], 1).to(ctx.device)
+            ex = torch.randint(0, 777, (B,), generator=g).to(ctx.device)
+            y = (torch.rand(B, generator=g) < 0.3).float().to(ctx.device)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(model(ids, extra=ex), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        ctx.backend.engine.check()
+        model.eval()
+        with torch.no_grad():
+            probe = model(torch.stack([torch.arange(B) % v for v in vocab], 1).to(ctx.device),
+                          extra=(torch.arange(B) % 777).to(ctx.device)).cpu()
+        grp = getattr(model, "_embedding_group", None)
+        res.append((losses, probe, grp))
+    assert res[1][2] is not None and res[1][2].state == "on" and len(res[1][2].members) == 9, \
+        (res[1][2].state, len(res[1][2].members))       # 4 + 4 server tables (vocab > 100) + extra
+    assert res[0][0][-1] < res[0][0][0]
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) < 1e-5, (res[0][0], res[1][0])
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-5)

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_host_tier.py -x -q 2>&1 | tail -25
+timeout 600 python -m pytest tests/test_gpu_model.py -x -q 2>&1 | tail -25
