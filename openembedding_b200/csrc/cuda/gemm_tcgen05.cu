@@ -29,6 +29,8 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -350,6 +352,293 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
 }
 
+// =====================================================================================================
+// Persistent GEMM CHAIN: several dependent GEMMs of the training step in ONE launch.
+//
+// The dense side of a CTR step is nine small GEMMs (M = batch 4096, N / K in {448, 1728}); launched one by one
+// every kernel pays launch + barrier init + TMEM allocation + pipeline fill + epilogue drain + a partial last
+// wave for 5-30 us of tensor work, and a layer cannot start before the previous kernel has fully drained.
+// Here the tiles of all GEMMs of a chain (forward: fwd1 -> fwd2 -> fwd3; backward: dX3, dW3, dX2, dW2, dX1, dW1)
+// form ONE static work list consumed by persistent CTAs (two per SM):
+//   * set-up once per CTA; the TMA -> MMA smem ring and its phases run on ACROSS tiles;
+//   * TMEM holds TWO accumulators: the epilogue of tile i (tcgen05.ld, fused math, TMA store) overlaps the
+//     main loop of tile i+1;
+//   * dependencies are per 128-row block, not per kernel: a tile of layer l+1 starts as soon as the row block of
+//     layer l it reads is complete (`ready` counters, release / acquire at gpu scope + async-proxy fences) -- the
+//     batch-parallel structure of an MLP (row blocks are independent through forward AND backward) pipelines
+//     naturally; the split-K weight-gradient tiles wait for the row blocks of their K range only;
+//   * the static order puts every producer before its consumers, and each CTA walks its items in increasing order,
+//     so the smallest unfinished item can always run: no deadlock.
+// Tile code (TMA boxes, UMMA descriptors, fused epilogues) is the one of exb_gemm_tcgen05_kernel<64>.
+constexpr int CH_STAGES = 3;                  // 3 x 24 KB ring + 32 KB epilogue staging: two CTAs per SM
+constexpr int CH_BN = 64;
+constexpr int CH_B_BYTES = CH_BN * BK * 2;
+constexpr int CH_MAX_PROB = 8;
+constexpr int CH_MAX_MB = 64;                 // row blocks per problem tracked by the ready counters
+
+struct ChainMaps { CUtensorMap tmA, tmB, tmO; };
+struct ChainMapsAll { ChainMaps m[CH_MAX_PROB]; };    // passed as a __grid_constant__ parameter (3 KB): descriptors in param space
+struct ChainMeta {
+    GemmEpi E;
+    int m_tiles, n_tiles, splits, nkb, per;
+    int item0, items;
+    int dep, dep_kind, dep_need;              // dep_kind 0 none | 1 A rows = my row block | 2 my K range (batch rows)
+    int signal;
+};
+
+__device__ __forceinline__ void ch_decode(const ChainMeta* M, int nprob, int item, int& p, int& m, int& n, int& z) {
+    p = 0;
+#pragma unroll 1
+    for (int i = 1; i < nprob; ++i)
+        if (item >= M[i].item0) p = i;
+    const int local = item - M[p].item0;
+    const int mn = M[p].m_tiles * M[p].n_tiles;
+    z = local / mn;
+    const int r = local - z * mn;
+    m = r / M[p].n_tiles;
+    n = r - m * M[p].n_tiles;
+}
+__device__ __forceinline__ unsigned ch_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+exb_gemm_chain_kernel(const __grid_constant__ ChainMapsAll MAPS, const ChainMeta* __restrict__ metas, int nprob, int total_items,
+                      unsigned* __restrict__ ready, int* __restrict__ err) {
+    const ChainMaps* maps = MAPS.m;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + CH_STAGES * A_BYTES;
+    uint8_t* sStage = sB + CH_STAGES * CH_B_BYTES;                 // 4 warps x 8 KB (1024-byte aligned)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + 4 * 8192);
+    uint64_t* empty = full + CH_STAGES;
+    uint64_t* tfull = empty + CH_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    ChainMeta* M = reinterpret_cast<ChainMeta*>(tmem_slot + 4);
+
+    exb::pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < nprob * (int)(sizeof(ChainMeta) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(M)[i] = reinterpret_cast<const uint32_t*>(metas)[i];     // host-written
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < CH_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // two 64-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    exb::pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer
+            uint32_t kiter = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                int p, m_blk, n_blk, z;
+                ch_decode(M, nprob, item, p, m_blk, n_blk, z);
+                const ChainMeta& Q = M[p];
+                const int kb0 = z * Q.per, kb1 = min(Q.nkb, kb0 + Q.per);
+                if (Q.dep_kind) {      // the row blocks this tile reads must be complete
+                    int mb0 = m_blk, mb1 = m_blk + 1;
+                    if (Q.dep_kind == 2) { mb0 = (kb0 * BK) / BM; mb1 = (kb1 * BK + BM - 1) / BM; }
+                    const unsigned* cnt = ready + Q.dep * CH_MAX_MB;
+                    for (int mb = mb0; mb < mb1; ++mb) {
+                        uint32_t it = 0;
+                        while (ch_ld_acquire(cnt + mb) < (unsigned)Q.dep_need) {
+                            __nanosleep(64);
+                            if (++it > (1u << 22)) { atomicCAS(err, 0, 100 + p); break; }
+                        }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");   // generic acquire -> async-proxy (TMA) reads
+                }
+                const CUtensorMap* tA = &maps[p].tmA;
+                const CUtensorMap* tB = &maps[p].tmB;
+                for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+                    const int s = kiter % CH_STAGES;
+                    const uint32_t ph = (kiter / CH_STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], A_BYTES + CH_B_BYTES);
+                    if (Q.E.mn_major) {
+                        tma_load_2d(sA + s * A_BYTES, tA, &full[s], m_blk * BM, kb * BK);
+                        tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, tA, &full[s], m_blk * BM + 64, kb * BK);
+                        tma_load_2d(sB + s * CH_B_BYTES, tB, &full[s], n_blk * CH_BN, kb * BK);
+                    } else {
+                        tma_load_2d(sA + s * A_BYTES, tA, &full[s], kb * BK, m_blk * BM);
+                        tma_load_2d(sB + s * CH_B_BYTES, tB, &full[s], kb * BK, n_blk * CH_BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CH_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t kiter = 0, lit = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lit) {
+                int p, m_blk, n_blk, z;
+                ch_decode(M, nprob, item, p, m_blk, n_blk, z);
+                const ChainMeta& Q = M[p];
+                const int kb0 = z * Q.per, kb1 = min(Q.nkb, kb0 + Q.per);
+                const uint32_t acc = lit & 1u;
+                mbar_wait(&tempty[acc], ((lit >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + acc * CH_BN;
+                for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+                    const int s = kiter % CH_STAGES;
+                    const uint32_t ph = (kiter / CH_STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * CH_B_BYTES);
+                    if (Q.E.mn_major) {
+                        const uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tacc, umma_desc_mn(a0 + k * 2048, 8192), umma_desc_mn(b0 + k * 2048, 8192),
+                                      idesc_mn, ((kb - kb0) | k) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tacc, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc, ((kb - kb0) | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue warps (TMEM lane quadrant q), one 32-row x 64-column quarter of every tile
+        const int q = warp & 3;
+        uint8_t* wstage = sStage + (warp - 2) * 8192;
+        uint32_t lit = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lit) {
+            int p, m_blk, n_blk, z;
+            ch_decode(M, nprob, item, p, m_blk, n_blk, z);
+            const ChainMeta& Q = M[p];
+            const GemmEpi& E = Q.E;
+            const uint32_t acc = lit & 1u;
+            const int row0 = m_blk * BM + q * 32, row = row0 + lane;
+            const bool rv = row < E.M;
+            const bool f32out = (E.mode == EPI_DW || E.mode == EPI_DX_FM);
+            const CUtensorMap* tO = &maps[p].tmO;
+            bool waited = false;
+#pragma unroll 1
+            for (int c0 = 0; c0 < CH_BN; c0 += 32) {
+                const int n0 = n_blk * CH_BN + c0;
+                uint4 mk[4];
+                float4 e4[8], s4[8];
+                float dl = 0.f;
+                if (E.mode == EPI_DX && rv) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(E.mask + (size_t)row * E.ldmask + n0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mk[j] = mp[j];
+                }
+                const bool fm = (E.mode == EPI_DX_FM) && rv && (n0 + 31 < E.fm_cols);
+                if (fm) {
+                    const float4* ep = reinterpret_cast<const float4*>(E.emb + (size_t)row * E.ldemb + n0);
+                    const float* sbase = E.S + (size_t)row * E.D;
+                    dl = E.dlogit[row];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        e4[j] = ep[j];
+                        s4[j] = *reinterpret_cast<const float4*>(sbase + ((n0 + 4 * j) % E.D));
+                    }
+                }
+                if (!waited) {
+                    mbar_wait(&tfull[acc], (lit >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    waited = true;
+                }
+                uint32_t v[32];
+                tmem_ld32(tmem_base + acc * CH_BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (c0 + 32 >= CH_BN) {          // last read of this accumulator: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[acc])) : "memory");
+                }
+                const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(mk);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    const int n = n0 + j;
+                    if (E.mode == EPI_FWD) {
+                        if (E.relu) x = fmaxf(x, 0.f);
+                        if (n == E.ones_col) x = 1.f;
+                        if (n >= E.N) x = 0.f;
+                    } else if (E.mode == EPI_DX) {
+                        if (!rv || !(__bfloat162float(mh[j]) > 0.f) || n == E.ones_col || n >= E.N) x = 0.f;
+                    } else if (fm) {
+                        const float* ef = reinterpret_cast<const float*>(e4);
+                        const float* sf = reinterpret_cast<const float*>(s4);
+                        x += dl * (sf[j] - ef[j]);
+                    }
+                    v[j] = __float_as_uint(x);
+                }
+                if (f32out) {
+                    uint8_t* tile = wstage + (c0 >> 5) * 4096;       // [32 rows][32 fp32]
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        *reinterpret_cast<uint4*>(tile + lane * 128 + ((t ^ (lane & 7)) << 4)) =
+                            make_uint4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (E.mode == EPI_DW)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(tO), "r"(smem_u32(tile)), "r"(n0), "r"(row0) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(tO), "r"(smem_u32(tile)), "r"(n0), "r"(row0) : "memory");
+                    }
+                } else {
+                    uint8_t* tile = wstage;                            // [32 rows][64 bf16]
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * u]), __uint_as_float(v[8 * t + 2 * u + 1]));
+                            pk[u] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const int chunk = (c0 >> 3) + t;
+                        *reinterpret_cast<uint4*>(tile + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+            if (!f32out) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(tO), "r"(smem_u32(wstage)), "r"(n_blk * CH_BN), "r"(row0) : "memory");
+            }
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // writes complete (the staging tile is free, too)
+                if (Q.signal) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    atomicAdd(&ready[p * CH_MAX_MB + m_blk], 1u);
+                }
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -497,5 +786,121 @@ int exb_gemm_bf16_tn(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     if (err != cudaSuccess) { g_gemm_err = std::string("gemm_tn launch: ") + cudaGetErrorString(err); return -1; }
     return 0;
 }
+
+// ---------------------------------------------------------------- GEMM chains (persistent, one launch)
+struct ChainDesc {      // one GEMM of a chain (python: ops/gemm.py ChainDesc)
+    int tn;             // 0: D = A[M,K] B[N,K]^T (K-major operands); 1: D[M,N] += A[K,M]^T B[K,N] (split-K, fp32 reduce-add)
+    int M, N, K;
+    unsigned long long A, B, out;
+    long long lda, ldb, ldo;
+    int mode, relu, ones_col, fm_cols, D, splits;
+    unsigned long long mask; long long ldmask;
+    unsigned long long dlogit, S, emb; long long ldemb;
+    int dep, dep_kind;  // index of the GEMM of this chain that produces this one's A operand (-1: none); kind 1 row block, 2 K range
+};
+struct Chain {
+    int nprob = 0, total = 0, grid = 0;
+    ChainMapsAll maps;
+    ChainMeta* d_meta = nullptr;
+    unsigned* d_ready = nullptr;
+    int* d_err = nullptr;
+    size_t smem = 0;
+};
+
+int exb_chain_desc_size() { return (int)sizeof(ChainDesc); }
+
+void* exb_chain_create(const void* descs, int n, int sms) {
+    if (n < 1 || n > CH_MAX_PROB) { g_gemm_err = "chain: 1..8 GEMMs"; return nullptr; }
+    const ChainDesc* D = reinterpret_cast<const ChainDesc*>(descs);
+    std::vector<ChainMaps> maps(n);
+    std::vector<ChainMeta> meta(n);
+    int item0 = 0;
+    for (int i = 0; i < n; ++i) {
+        const ChainDesc& d = D[i];
+        ChainMeta& Q = meta[i];
+        memset(&Q, 0, sizeof(Q));
+        if (d.K % BK != 0 || d.lda % 8 != 0 || d.ldb % 8 != 0) { g_gemm_err = "chain: K % 64 / ld % 8 violated"; return nullptr; }
+        GemmEpi& E = Q.E;
+        E.mode = d.tn ? EPI_DW : d.mode; E.relu = d.relu; E.ones_col = d.tn ? -1 : d.ones_col; E.fm_cols = d.fm_cols;
+        E.M = d.M; E.N = d.N; E.D = d.D > 0 ? d.D : 1; E.mn_major = d.tn ? 1 : 0;
+        E.out = (void*)d.out; E.ldo = d.ldo; E.outT = nullptr; E.ldoT = 0;
+        E.mask = (const __nv_bfloat16*)d.mask; E.ldmask = d.ldmask;
+        E.dlogit = (const float*)d.dlogit; E.S = (const float*)d.S; E.emb = (const float*)d.emb; E.ldemb = d.ldemb;
+        E.swap = 0; E._pad2 = 0; E.dbg = nullptr;
+        const bool f32out = (E.mode == EPI_DW || E.mode == EPI_DX_FM);
+        bool ok;
+        if (d.tn) {
+            ok = make_map_ex(&maps[i].tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)d.A, d.K, d.M, d.lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                 make_map_ex(&maps[i].tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)d.B, d.K, d.N, d.ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+        } else {
+            ok = make_map(&maps[i].tmA, (const void*)d.A, d.M, d.K, d.lda, BM) && make_map(&maps[i].tmB, (const void*)d.B, d.N, d.K, d.ldb, CH_BN);
+        }
+        if (ok) {
+            if (f32out) ok = make_map_ex(&maps[i].tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (const void*)d.out, d.M, d.N, d.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+            else ok = make_map_ex(&maps[i].tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (const void*)d.out, d.M, (d.N + 63) / 64 * 64, d.ldo, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        }
+        if (!ok) return nullptr;
+        Q.nkb = d.K / BK;
+        int splits = d.tn ? std::max(1, d.splits) : 1;
+        if (splits > Q.nkb) splits = Q.nkb;
+        Q.per = (Q.nkb + splits - 1) / splits;
+        Q.splits = (Q.nkb + Q.per - 1) / Q.per;
+        Q.m_tiles = (d.M + BM - 1) / BM; Q.n_tiles = (d.N + CH_BN - 1) / CH_BN;
+        Q.item0 = item0; Q.items = Q.m_tiles * Q.n_tiles * Q.splits;
+        item0 += Q.items;
+        Q.dep = d.dep; Q.dep_kind = d.dep >= 0 ? d.dep_kind : 0; Q.dep_need = 0; Q.signal = 0;
+        if (Q.dep_kind) {
+            if (d.dep >= i) { g_gemm_err = "chain: a GEMM may only depend on an earlier one"; return nullptr; }
+            meta[d.dep].signal = 1;
+            Q.dep_need = 4 * meta[d.dep].n_tiles;      // four epilogue warps sign off every tile of the row block
+            if (meta[d.dep].m_tiles > CH_MAX_MB) { g_gemm_err = "chain: too many row blocks"; return nullptr; }
+        }
+    }
+    Chain* c = new Chain();
+    c->nprob = n; c->total = item0;
+    c->smem = CH_STAGES * (A_BYTES + CH_B_BYTES) + 4 * 8192 + (2 * CH_STAGES + 4) * 8 + 16 + CH_MAX_PROB * sizeof(ChainMeta) + 1024;
+    cudaFuncSetAttribute(exb_gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+    cudaFuncSetAttribute(exb_gemm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // two CTAs per SM by construction: 2 x (smem + 1 KB reserved) <= 228 KB, 2 x 192 threads x 168 registers <= 64 K
+    // (the occupancy API answers 1 here when it is asked before the carve-out is configured)
+    int occ = (2 * (c->smem + 1024) <= 232448) ? 2 : 1;
+    if (const char* ev = getenv("EXB_CHAIN_CTAS_PER_SM")) occ = std::max(1, std::min(2, atoi(ev)));
+    // dependencies are spin-waits: every CTA has to be resident
+    c->grid = std::min(c->total, (sms > 0 ? sms : 148) * occ);
+    memset(&c->maps, 0, sizeof(c->maps));
+    for (int i = 0; i < n; ++i) c->maps.m[i] = maps[i];
+    if (cudaMalloc(&c->d_meta, n * sizeof(ChainMeta)) != cudaSuccess ||
+        cudaMalloc(&c->d_ready, CH_MAX_PROB * CH_MAX_MB * 4) != cudaSuccess || cudaMalloc(&c->d_err, 4) != cudaSuccess) {
+        g_gemm_err = "chain: cudaMalloc failed"; delete c; return nullptr;
+    }
+    cudaMemcpy(c->d_meta, meta.data(), n * sizeof(ChainMeta), cudaMemcpyHostToDevice);
+    cudaMemset(c->d_ready, 0, CH_MAX_PROB * CH_MAX_MB * 4);
+    cudaMemset(c->d_err, 0, 4);
+    return c;
+}
+void exb_chain_destroy(void* h) {
+    Chain* c = (Chain*)h;
+    cudaFree(c->d_meta); cudaFree(c->d_ready); cudaFree(c->d_err);
+    delete c;
+}
+int exb_chain_launch(void* h, uint64_t stream) {
+    Chain* c = (Chain*)h;
+    cudaError_t err = cudaMemsetAsync(c->d_ready, 0, CH_MAX_PROB * CH_MAX_MB * 4, (cudaStream_t)stream);
+    if (err == cudaSuccess)
+        err = exb::launch_pdl(exb_gemm_chain_kernel, dim3(c->grid), dim3(NUM_THREADS), c->smem, (cudaStream_t)stream,
+                              c->maps, (const ChainMeta*)c->d_meta, c->nprob, c->total, c->d_ready, c->d_err);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err != cudaSuccess) { g_gemm_err = std::string("chain launch: ") + cudaGetErrorString(err); return -1; }
+    return 0;
+}
+// device sync; returns the error word (0 ok, 100 + p: GEMM p timed out waiting for its producer)
+int exb_chain_status(void* h) {
+    Chain* c = (Chain*)h;
+    int v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, c->d_err, 4, cudaMemcpyDeviceToHost);
+    return v;
+}
+int exb_chain_info(void* h, int* out) { Chain* c = (Chain*)h; out[0] = c->total; out[1] = c->grid; out[2] = (int)c->smem; return 0; }
 
 }  // extern "C"

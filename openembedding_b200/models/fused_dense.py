@@ -239,6 +239,34 @@ class FusedCTR:
             oa.mat[l].Wb, oa.mat[l].WTb = self.Wb[l].data_ptr(), self.WTb[l].data_ptr()
         self._opt_args = oa
         self._grad_dirty = False
+        # persistent GEMM chains: forward (fwd1 -> ... -> fwdL) and backward (dX / dW of every layer) in ONE launch
+        # each (csrc/cuda/gemm_tcgen05.cu: exb_gemm_chain_kernel). EXB_GEMM_CHAIN=0: one launch per GEMM.
+        mode = os.environ.get("EXB_GEMM_CHAIN", "bwd")          # "0" | "bwd" | "1" (forward and backward)
+        self.use_chain = mode != "0" and self.mn_major and L <= 4
+        self.chain_fwd = self.use_chain and mode == "1"
+        self.fwd_chain = self.bwd_chain = None
+        if self.use_chain:
+            fd, src = [], self.A0
+            for l in range(L):
+                fd.append(G.chain_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
+                                     ones_col=self.Hp[l] - 1, dep=l - 1))
+                src = self.H[l]
+            self.fwd_chain = G.GemmChain(fd, dev)
+            bd, prod = [], -1          # prod: index (in the chain) of the GEMM that produced dZ[l]
+            for l in range(L - 1, -1, -1):
+                gW = self.gview("W%d" % l).view(self.Hp[l], dims[l])
+                if l > 0:
+                    bd.append(G.chain_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
+                                         ones_col=self.Hp[l - 1] - 1, mask=self.H[l - 1], dep=prod))
+                else:
+                    bd.append(G.chain_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM,
+                                         dlogit=self.dlogit, S=self.S, emb=self.X32,
+                                         fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, dep=prod))
+                nxt = len(bd) - 1
+                bd.append(G.chain_tn(self.dZ[l], self.A0 if l == 0 else self.H[l - 1], self.Hp[l], dims[l], B, gW,
+                                     splits=self.dw_splits, dep=prod))
+                prod = nxt
+            self.bwd_chain = G.GemmChain(bd, dev)
         self.refresh_weights()
         torch.cuda.synchronize(dev)
 
@@ -308,10 +336,13 @@ class FusedCTR:
         self._mark("prep")
         dims = [self.K0p] + self.Hp
         src = self.A0
-        for l in range(L):
-            G.gemm_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
-                      ones_col=self.Hp[l] - 1, outT=self.HT[l] if (l < L - 1 and not tn) else None, stream=st)
-            src = self.H[l]
+        if self.chain_fwd:
+            self.fwd_chain.launch(st)
+        else:
+            for l in range(L):
+                G.gemm_nt(src, self.Wb[l], B, self.Hp[l], dims[l], self.H[l], mode=G.EPI_FWD, relu=True,
+                          ones_col=self.Hp[l] - 1, outT=self.HT[l] if (l < L - 1 and not tn) else None, stream=st)
+                src = self.H[l]
         self._mark("fwd_gemm")
         row_head = tn and self.Hp[-1] <= 512       # merged row-wise head; cachegrad then owns the cached linear grads
         ha = _HeadArgs(self.H[-1].data_ptr(), self.Hp[-1], self.Hp[-1] - 1, self.view("wout").data_ptr(),
@@ -323,11 +354,14 @@ class FusedCTR:
                        0 if row_head else self.gview("cache_lin").data_ptr(), B, 1.0 / B)
         _ck(lib.exb_head(ctypes.byref(ha), B, st), "head")
         self._mark("head")
-        for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
-            G.gemm_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
-                      ones_col=self.Hp[l - 1] - 1, outT=None if tn else self.dZT[l - 1], mask=self.H[l - 1], stream=st)
-        G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
-                  S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
+        if self.use_chain:
+            self.bwd_chain.launch(st)          # dX and dW of every layer: one persistent launch
+        else:
+            for l in range(L - 1, 0, -1):      # dZ_{l-1} = (dZ_l @ W_l) * relu'(H_{l-1})
+                G.gemm_nt(self.dZ[l], self.WTb[l], B, self.Hp[l - 1], self.Hp[l], self.dZ[l - 1], mode=G.EPI_DX,
+                          ones_col=self.Hp[l - 1] - 1, outT=None if tn else self.dZT[l - 1], mask=self.H[l - 1], stream=st)
+            G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
+                      S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
         self._mark("dx_gemm")
         if side_used:        # the plan(s) built on the side stream are complete before the push reads / flips the slots
             torch.cuda.current_stream(self.dev).wait_event(self._ev_plan)
@@ -339,7 +373,7 @@ class FusedCTR:
                 self._s2.wait_event(self._ev_fork)
                 self.group.push_update(ids, self.G32)
                 self._ev_join.record(self._s2)
-        for l in range(L):                 # dW_l = dZ_l^T @ H_{l-1}
+        for l in range(L if not self.use_chain else 0):                 # dW_l = dZ_l^T @ H_{l-1}
             prevT = self.A0T if l == 0 else self.HT[l - 1]
             gW = self.gview("W%d" % l).view(self.Hp[l], dims[l])
             if tn:
@@ -379,7 +413,8 @@ class FusedCTR:
         L = len(self.hidden)
         prep = 1 if (self.mn_major and 128 % self.Dp == 0) else 2
         head = 1 if (self.mn_major and self.Hp[-1] <= 512) else 2
-        n = 1 + prep + L + head + L + L + (1 if self.nc else 0) + 1 + 1   # pull prep fwd head dX dW cache push optimizer
+        gemms = (1 if self.chain_fwd else L) + (1 if self.use_chain else 2 * L)   # persistent chains: fwd, bwd
+        n = 1 + prep + gemms + head + (1 if self.nc else 0) + 1 + 1      # pull prep GEMMs head cache push optimizer
         return n + (1 if self._ar is not None else 0)
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)

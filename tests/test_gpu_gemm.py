@@ -88,3 +88,66 @@ def test_dw_mn_major(M, N, K, splits):
     torch.cuda.synchronize()
     ref = A[:, :M].float().t() @ B[:, :N].float()
     assert torch.allclose(out[:, :N], ref, atol=5e-2, rtol=2e-2), (out[:, :N] - ref).abs().max()
+
+
+@pytest.mark.parametrize("M", [512, 4096])
+def test_chain_matches_single_launches(M):
+    """persistent chain (forward 3 layers; backward dX/dW of 3 layers with row-block dependencies) == the same GEMMs
+    launched one by one, bit for bit (same tiles, same K order)"""
+    from openembedding_b200.ops import gemm as G
+    K0, H1, H2, H3 = 320, 192, 192, 128
+    dev = torch.device("cuda")
+    A0 = _mk(M, K0, seed=1)
+    W = [_mk(H1, K0, scale=0.1, seed=2), _mk(H2, H1, scale=0.1, seed=3), _mk(H3, H2, scale=0.1, seed=4)]
+    WT = [w.t().contiguous() for w in W]
+    dims = [K0, H1, H2, H3]
+
+    def run(chain):
+        H = [torch.zeros(M, d, device=dev, dtype=torch.bfloat16) for d in dims[1:]]
+        dZ = [torch.zeros(M, d, device=dev, dtype=torch.bfloat16) for d in dims[1:]]
+        dZ[2].copy_(_mk(M, H3, scale=0.05, seed=9))
+        gW = [torch.zeros(dims[l + 1], dims[l], device=dev, dtype=torch.float32) for l in range(3)]
+        G32 = torch.zeros(M, K0, device=dev, dtype=torch.float32)
+        if chain:
+            src, fd = A0, []
+            for l in range(3):
+                fd.append(G.chain_nt(src, W[l], M, dims[l + 1], dims[l], H[l], mode=G.EPI_FWD, relu=True, ones_col=dims[l + 1] - 1, dep=l - 1))
+                src = H[l]
+            c1 = G.GemmChain(fd, dev)
+            c1.launch()
+            bd, prod = [], -1
+            for l in (2, 1, 0):
+                if l > 0:
+                    bd.append(G.chain_nt(dZ[l], WT[l], M, dims[l], dims[l + 1], dZ[l - 1], mode=G.EPI_DX, ones_col=dims[l] - 1,
+                                         mask=H[l - 1], dep=prod))
+                else:
+                    bd.append(G.chain_nt(dZ[0], WT[0], M, K0, H1, G32, mode=G.EPI_DX_FM, fm_cols=0, D=4, dep=prod))
+                nxt = len(bd) - 1
+                bd.append(G.chain_tn(dZ[l], A0 if l == 0 else H[l - 1], dims[l + 1], dims[l], M, gW[l], splits=4, dep=prod))
+                prod = nxt
+            c2 = G.GemmChain(bd, dev)
+            c2.launch()
+            c1.check(); c2.check()
+            c1.close(); c2.close()
+        else:
+            src = A0
+            for l in range(3):
+                G.gemm_nt(src, W[l], M, dims[l + 1], dims[l], H[l], mode=G.EPI_FWD, relu=True, ones_col=dims[l + 1] - 1)
+                src = H[l]
+            for l in (2, 1):
+                G.gemm_nt(dZ[l], WT[l], M, dims[l], dims[l + 1], dZ[l - 1], mode=G.EPI_DX, ones_col=dims[l] - 1, mask=H[l - 1])
+            G.gemm_nt(dZ[0], WT[0], M, K0, H1, G32, mode=G.EPI_DX_FM, fm_cols=0, D=4)
+            for l in range(3):
+                G.gemm_tn(dZ[l], A0 if l == 0 else H[l - 1], dims[l + 1], dims[l], M, gW[l], splits=4)
+        torch.cuda.synchronize()
+        return H, dZ, gW, G32
+
+    a, b = run(False), run(True)
+    for l in range(3):
+        assert torch.equal(a[0][l], b[0][l]), ("H", l, float((a[0][l].float() - b[0][l].float()).abs().max()))
+        assert torch.equal(a[1][l], b[1][l]), ("dZ", l)
+        assert torch.allclose(a[2][l], b[2][l], atol=1e-3, rtol=1e-4), ("gW", l, float((a[2][l] - b[2][l]).abs().max()))
+    assert torch.equal(a[3], b[3])
+    ref = torch.relu(A0.float() @ W[0].float().t())
+    ref[:, H1 - 1] = 1.0
+    assert torch.allclose(b[0][0].float(), ref, atol=3e-2, rtol=3e-2)

@@ -1,3 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_model.py -x -q 2>&1 | tail -25
+for mode in bwd 1 0; do
+EXB_GEMM_CHAIN=$mode timeout 400 python bench.py --steps 200 --warmup 20 > gpurun_out/r2_q_$mode.log 2>&1; echo "mode=$mode rc=$?"
+grep '^{' gpurun_out/r2_q_$mode.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['final_loss'])"
+done
