@@ -300,10 +300,36 @@ class CudaBackend:
         todo = [m for m in (metas or self.vars) if not m.allocated]
         if not todo:
             return
+        self._check_memory_limits(todo)
         for m in todo:
             self.engine.alloc(m.handle)
             m.allocated = True
         self.engine.connect(self.group)
+
+    soft_limit_mb = hard_limit_mb = 0
+
+    def _check_memory_limits(self, todo):
+        """ShardStorageMemory analogue: refuse (hard) / warn about (soft) allocations beyond the configured budget"""
+        if not (self.soft_limit_mb or self.hard_limit_mb):
+            return
+        from .status import Status, StatusError
+        from .utils import log
+        held = self.engine.memory_info()
+        want = held["tables_bytes"] + held["plans_bytes"] + sum(self.engine.table_bytes_estimate(m.handle) for m in todo)
+        if self.hard_limit_mb and want > self.hard_limit_mb << 20:
+            raise StatusError(Status.OOM, "sparse engine would hold %d MB, server.memory_hard_limit_mb is %d"
+                              % (want >> 20, self.hard_limit_mb))
+        if self.soft_limit_mb and want > self.soft_limit_mb << 20:
+            log.warning("sparse engine holds %d MB, above server.memory_soft_limit_mb = %d" % (want >> 20, self.soft_limit_mb))
+
+    def memory_info(self):
+        info = self.engine.memory_info()
+        from .host_tier import _tiers
+        tiers = {vid: t.memory() for vid, t in _tiers.items() if hasattr(t, "memory")}
+        info["tiers"] = tiers
+        info["tiers_bytes"] = sum(t["hbm_index_bytes"] for t in tiers.values())
+        info["pinned_host_bytes"] = sum(t["pinned_host_bytes"] for t in tiers.values())
+        return info
 
     def _plan_for(self, meta, n):
         """Per-variable plan of capacity next_pow2(n). Creating a plan is collective (IPC exchange) and the

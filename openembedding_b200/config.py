@@ -280,6 +280,10 @@ _ENV_DEFAULTS = {
         "update_early_return": True,
         # B200 engine additions
         "hash_table_reserve": 1 << 20, "host_tier_root_path": "", "deterministic": False,
+        # HBM accounting (reference: ShardStorageMemory soft / hard limits, pico-ps storage/Storage.h:261-289): MB of
+        # device memory the sparse engine of ONE rank may hold (tables + optimizer state + plans + tier caches);
+        # 0 = unlimited. Above the soft limit a warning is logged, above the hard limit allocation fails with OOM.
+        "memory_soft_limit_mb": 0, "memory_hard_limit_mb": 0,
         "hash_table_grow_interval": 64, "hash_table_max_load": 0.5,
     },
 }

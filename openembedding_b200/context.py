@@ -49,6 +49,8 @@ class Context:
             self.backend.hash_reserve = int(self.env["server"]["hash_table_reserve"])
             self.backend.grow_interval = int(self.env["server"]["hash_table_grow_interval"])
             self.backend.max_load = float(self.env["server"]["hash_table_max_load"])
+            self.backend.soft_limit_mb = int(self.env["server"]["memory_soft_limit_mb"])
+            self.backend.hard_limit_mb = int(self.env["server"]["memory_hard_limit_mb"])
         else:
             if self.dist_on and dist.get_backend() != "gloo":
                 self.group = dist.new_group(backend="gloo")
@@ -123,6 +125,11 @@ class Context:
         tick = getattr(self.backend, "tick", None)
         if tick is not None:
             tick(n)
+
+    def memory_info(self):
+        """device / pinned-host memory held by the sparse engine of this rank (tables, plans, host tiers)"""
+        fn = getattr(self.backend, "memory_info", None)
+        return fn() if fn is not None else {}
 
     def model_sign(self):
         return "%s-%d" % (self.model_uuid, int(self.model_version))

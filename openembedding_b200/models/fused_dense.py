@@ -28,6 +28,7 @@ import torch
 from .. import _native
 from ..context import get_context
 from ..ops import gemm as G
+from ..utils import timers as _timers
 
 
 class _PrepArgs(ctypes.Structure):
@@ -285,6 +286,7 @@ class FusedCTR:
     _trace = None          # list of (name, event) when stage tracing is on (tools/mp_timeline.py)
 
     def _mark(self, name):
+        _timers.nvtx_mark(name)              # EXB_NVTX=1: stage boundaries on the nsys / ncu timeline
         if self._trace is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream(self.dev))

@@ -63,10 +63,13 @@ class Trainer:
 
     # ---- one device step on given device tensors; returns loss tensor (0-dim, device)
     def _device_step(self, ids, dense, labels):
+        from ..utils.timers import nvtx_range
         self.opt.zero_grad()
-        logits = self.model(ids, dense)
-        loss = F.binary_cross_entropy_with_logits(logits, labels)
-        loss.backward()
+        with nvtx_range("forward"):
+            logits = self.model(ids, dense)
+            loss = F.binary_cross_entropy_with_logits(logits, labels)
+        with nvtx_range("backward+push_update"):
+            loss.backward()
         if self.world > 1:
             if self._ar is not None:
                 self._ar()

@@ -178,6 +178,36 @@ class CudaEngine:
                   feat_offsets2=None, feat_split=None):
         return SparsePlan(self, feat_tables, batch, feat_offsets, io_stride, feat_cols, ncols, feat_offsets2, feat_split)
 
+    # --------------------------------------------------------------- memory accounting
+    def memory_info(self):
+        """Bytes of device memory held by this rank's engine (reference: pico_memory accounting + the MEMORY_INFO
+        request, pico-ps service/Service.cpp:511-518)."""
+        tables = []
+        for t, meta in enumerate(self.tables):
+            if not meta["allocated"]:
+                tables.append({"table": t, "allocated": False, "bytes": 0})
+                continue
+            info = self.table_info(t)
+            state = int(info["rows"]) * int(info["sstride"]) * 4
+            touched = 0 if meta["is_hash"] else (int(info["rows"]) + 31) // 32 * 4
+            tables.append({"table": t, "allocated": True, "rows": int(info["rows"]), "dim": meta["dim"],
+                           "hash": meta["is_hash"], "weights": int(info["w_bytes"]), "keys": int(info["keys_bytes"]),
+                           "state": state, "bytes": int(info["w_bytes"]) + int(info["keys_bytes"]) + state + touched})
+        plans = []
+        for p in self.plans:
+            if p.h:
+                inbox, work = p.memory()
+                plans.append({"features": p.F, "batch": p.B, "inbox": inbox, "work": work, "bytes": inbox + work})
+        free, total = torch.cuda.mem_get_info(self.device)
+        return {"tables": tables, "plans": plans, "tables_bytes": sum(t["bytes"] for t in tables),
+                "plans_bytes": sum(p["bytes"] for p in plans), "device_free": int(free), "device_total": int(total)}
+
+    def table_bytes_estimate(self, t):
+        """bytes exb_table_alloc will take for a not-yet-allocated table (rows are known at add time)"""
+        info = self.table_info(t)
+        rows, ws, ss = int(info["rows"]), int(info["wstride"]), int(info["sstride"])
+        return rows * (ws + ss) * 4 + (rows * 8 if self.tables[t]["is_hash"] else (rows + 31) // 32 * 4)
+
     # --------------------------------------------------------------- status
     def status(self):
         st = ctypes.c_int32(0)

@@ -140,3 +140,34 @@ class Monitor:
 
     def stop(self):
         self._stop.set()
+
+
+# ---- NVTX ranges ("CUDA events per phase ... NVTX ranges"). EXB_NVTX=1 turns them on; off they cost nothing.
+import os as _os
+
+nvtx_enabled = _os.environ.get("EXB_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    """``with nvtx_range("pull"):`` -- a named range on the timeline of nsys / ncu when EXB_NVTX=1"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *a):
+        if nvtx_enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx_mark(name):
+    if nvtx_enabled:
+        import torch
+        torch.cuda.nvtx.mark(name)

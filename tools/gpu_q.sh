@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for mode in bwd 1 0; do
-EXB_GEMM_CHAIN=$mode timeout 400 python bench.py --steps 200 --warmup 20 > gpurun_out/r2_q_$mode.log 2>&1; echo "mode=$mode rc=$?"
-grep '^{' gpurun_out/r2_q_$mode.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['final_loss'])"
-done
+timeout 900 python tools/loss_parity.py --steps 2000 --dim 16 > gpurun_out/r2_loss_parity.log 2>&1; echo rc=$?
+tail -1 gpurun_out/r2_loss_parity.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k: d[k] for k in ('first_window','last_window','fused_vs_fp32','bf16_baseline_vs_fp32')})" || tail -5 gpurun_out/r2_loss_parity.log
