@@ -90,17 +90,27 @@ class FusedEmbeddings(nn.Module):
         return self.group.pull(ids)
 
 
+def _gemm_layers(tc):
+    """(Linear, Conv1x1) layer classes: on the CUDA engine every GEMM-shaped op of the eager zoo runs on the
+    hand-written tcgen05 kernel (ops/tc_linear.py); on CPU plain torch"""
+    if tc:
+        from ..ops.tc_linear import TcConv1x1, TcLinear
+        return TcLinear, TcConv1x1
+    return nn.Linear, lambda cin, cout: nn.Conv1d(cin, cout, 1)
+
+
 class CIN(nn.Module):
     """Compressed Interaction Network (xDeepFM), DeepCTR defaults: split_half, relu."""
 
-    def __init__(self, num_fields, layer_sizes=(128, 128), split_half=True):
+    def __init__(self, num_fields, layer_sizes=(128, 128), split_half=True, tc=False):
         super().__init__()
+        _, Conv = _gemm_layers(tc)
         self.split_half = split_half
         self.layer_sizes = layer_sizes
         self.convs = nn.ModuleList()
         prev, total = num_fields, 0
         for i, size in enumerate(layer_sizes):
-            self.convs.append(nn.Conv1d(num_fields * prev, size, 1))
+            self.convs.append(Conv(num_fields * prev, size))
             if split_half and i != len(layer_sizes) - 1:
                 prev = size // 2
                 total += size // 2
@@ -124,9 +134,10 @@ class CIN(nn.Module):
 
 
 class CrossNetV2(nn.Module):
-    def __init__(self, dim, layers=3):
+    def __init__(self, dim, layers=3, tc=False):
         super().__init__()
-        self.w = nn.ModuleList([nn.Linear(dim, dim) for _ in range(layers)])
+        Linear, _ = _gemm_layers(tc)
+        self.w = nn.ModuleList([Linear(dim, dim) for _ in range(layers)])
 
     def forward(self, x0):
         x = x0
@@ -181,20 +192,24 @@ class CTRModel(nn.Module):
             self.cache_emb = nn.Parameter(torch.zeros(off, embedding_dim, device=ctx.device)) if self.has_emb else None
             self.cache_lin = nn.Parameter(torch.zeros(off, 1, device=ctx.device))
         dnn_in = nf * embedding_dim + num_dense
+        # GEMM-shaped layers on the hand-written tcgen05 kernel (bf16 operands) when the model computes in bf16 on CUDA
+        tc = ctx.device.type == "cuda" and compute_dtype == torch.bfloat16
+        self.tc = tc
+        Linear, _ = _gemm_layers(tc)
         self.dense_linear = nn.Linear(num_dense, 1, bias=False) if num_dense else None
         self.bias = nn.Parameter(torch.zeros(1))
         layers, prev = [], dnn_in
         if self.has_emb:
             for h in dnn_hidden:
-                layers += [nn.Linear(prev, h), nn.ReLU()]
+                layers += [Linear(prev, h), nn.ReLU()]
                 prev = h
             self.dnn = nn.Sequential(*layers)
             self.dnn_out = nn.Linear(prev, 1, bias=False)
         if self.model_name == "xdeepfm":
-            self.cin = CIN(nf, cin_layers)
+            self.cin = CIN(nf, cin_layers, tc=tc)
             self.cin_out = nn.Linear(self.cin.out_dim, 1, bias=False)
         if self.model_name == "dcn":
-            self.cross = CrossNetV2(dnn_in, cross_layers)
+            self.cross = CrossNetV2(dnn_in, cross_layers, tc=tc)
             self.dnn_out = nn.Linear(prev + dnn_in, 1, bias=False)
         self.to(ctx.device)
 
@@ -228,7 +243,7 @@ class CTRModel(nn.Module):
             return logit
         emb = torch.cat(embs, dim=1) if len(embs) > 1 else embs[0]        # [B, nf, D] fp32
         with torch.autocast(device_type=emb.device.type, dtype=self.compute_dtype,
-                            enabled=self.compute_dtype != torch.float32):
+                            enabled=self.compute_dtype != torch.float32 and not self.tc):
             x = torch.cat([emb.reshape(B, -1), dense], dim=1)
             if self.model_name == "dcn":
                 h = torch.cat([self.cross(x), self.dnn(x)], dim=1)

@@ -151,3 +151,28 @@ def test_chain_matches_single_launches(M):
     ref = torch.relu(A0.float() @ W[0].float().t())
     ref[:, H1 - 1] = 1.0
     assert torch.allclose(b[0][0].float(), ref, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 100, 40), (1000, 247, 400), (130, 64, 1)])
+def test_tc_linear_matches_torch(M, K, N):
+    """forward, dX, dW, db of TcLinear (tcgen05 GEMMs) vs nn.Linear in fp32"""
+    from openembedding_b200.ops.tc_linear import TcLinear
+    torch.manual_seed(0)
+    ref = torch.nn.Linear(K, N).cuda()
+    tc = TcLinear(K, N).cuda()
+    tc.load_state_dict(ref.state_dict())
+    x = torch.randn(M, K, device="cuda")
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn(M, N, device="cuda")
+    y1, y2 = ref(x1), tc(x2)
+    y1.backward(g)
+    y2.backward(g)
+    torch.cuda.synchronize()
+
+    def close(a, b, what):
+        err = float((a - b).abs().max())
+        assert err < 0.03 * float(b.abs().max()) + 1e-2, (what, err, float(b.abs().max()))
+    close(y2, y1, "y")
+    close(x2.grad, x1.grad, "dx")
+    close(tc.weight.grad, ref.weight.grad, "dw")
+    close(tc.bias.grad, ref.bias.grad, "db")
