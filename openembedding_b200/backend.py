@@ -406,16 +406,57 @@ class CudaBackend:
         return s if s < meta.shard_num else -1
 
     def iter_local_rows(self, meta, block_rows, with_state=True):
+        """Streaming dump (K8 of SURVEY 2.5): device key compaction, then the rows travel in CHUNKS of many file
+        blocks -- gather kernel into a device staging buffer, asynchronous D2H into one of two PINNED host buffers
+        on a copy stream -- while the caller writes the previous chunk's blocks: the copy of chunk i+1 overlaps the
+        file writes of chunk i. Yields (local indices, weights, states) per file block (views of the pinned buffer)."""
         self.ensure_allocated([meta])
         if self.shard_id(meta) < 0:
             return
-        ids = self.engine.enumerate_ids(meta.handle)   # K8: device key compaction
-        for i in range(0, ids.numel(), block_rows):
-            blk = ids[i:i + block_rows]
-            w, s = self.engine.gather_rows(meta.handle, blk, with_state=with_state)
-            local = (blk // meta.shard_num).cpu().numpy().astype(np.uint64)
-            yield local, w.cpu().numpy(), (s.cpu().numpy() if (with_state and s is not None)
-                                           else np.empty((blk.numel(), 0), dtype=np.float32))
+        ids = self.engine.enumerate_ids(meta.handle)   # device key compaction, sorted
+        n = int(ids.numel())
+        if n == 0:
+            return
+        sd = self.state_dim(meta) if with_state else 0
+        chunk = max(block_rows, min(n, block_rows * 64))
+        dev = self.device
+        copy = torch.cuda.Stream(device=dev)
+        pinned = [dict(i=torch.empty(chunk, dtype=torch.int64).pin_memory(),
+                       w=torch.empty((chunk, meta.dim), dtype=torch.float32).pin_memory(),
+                       s=torch.empty((chunk, max(sd, 1)), dtype=torch.float32).pin_memory(),
+                       ev=torch.cuda.Event()) for _ in range(2)]
+
+        def launch(c0, buf):
+            blk = ids[c0:c0 + chunk]
+            w, s = self.engine.gather_rows(meta.handle, blk, with_state=bool(sd))
+            cur = torch.cuda.current_stream(dev)
+            copy.wait_stream(cur)
+            with torch.cuda.stream(copy):
+                k = blk.numel()
+                buf["i"][:k].copy_(blk // meta.shard_num, non_blocking=True)
+                buf["w"][:k].copy_(w, non_blocking=True)
+                if sd:
+                    buf["s"][:k].copy_(s, non_blocking=True)
+                for t in (blk, w, s):
+                    if t is not None:
+                        t.record_stream(copy)
+                buf["ev"].record(copy)
+            return k
+
+        k_next = launch(0, pinned[0])
+        c0, which = 0, 0
+        while c0 < n:
+            buf, k = pinned[which], k_next
+            if c0 + chunk < n:
+                k_next = launch(c0 + chunk, pinned[which ^ 1])      # in flight while this chunk is written
+            buf["ev"].synchronize()
+            li = buf["i"].numpy().view(np.uint64)
+            wv, sv = buf["w"].numpy(), buf["s"].numpy()
+            for b0 in range(0, k, block_rows):
+                b1 = min(k, b0 + block_rows)
+                yield li[b0:b1], wv[b0:b1], (sv[b0:b1, :sd] if sd else np.empty((b1 - b0, 0), dtype=np.float32))
+            c0 += chunk
+            which ^= 1
 
     def read_rows(self, meta, global_ids):
         """(weights, states) of the given rows of this rank's shard (host tier write-back): device gather + D2H"""

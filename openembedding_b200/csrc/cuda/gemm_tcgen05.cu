@@ -637,6 +637,21 @@ exb_gemm_chain_kernel(const __grid_constant__ ChainMapsAll MAPS, const ChainMeta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
     }
+    // self-cleaning dependency counters: the LAST CTA to leave zeroes them for the next launch (no memset node in
+    // front of the kernel, so the launch keeps its programmatic-dependent-launch edge inside a CUDA graph)
+    if (warp == 0) {
+        unsigned last = 0;
+        if (lane == 0) {
+            __threadfence();
+            last = (atomicAdd(&ready[CH_MAX_PROB * CH_MAX_MB], 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            for (int i = lane; i < CH_MAX_PROB * CH_MAX_MB; i += 32) ready[i] = 0u;
+            __syncwarp();
+            if (lane == 0) { __threadfence(); ready[CH_MAX_PROB * CH_MAX_MB] = 0u; }
+        }
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -870,11 +885,11 @@ void* exb_chain_create(const void* descs, int n, int sms) {
     memset(&c->maps, 0, sizeof(c->maps));
     for (int i = 0; i < n; ++i) c->maps.m[i] = maps[i];
     if (cudaMalloc(&c->d_meta, n * sizeof(ChainMeta)) != cudaSuccess ||
-        cudaMalloc(&c->d_ready, CH_MAX_PROB * CH_MAX_MB * 4) != cudaSuccess || cudaMalloc(&c->d_err, 4) != cudaSuccess) {
+        cudaMalloc(&c->d_ready, (CH_MAX_PROB * CH_MAX_MB + 32) * 4) != cudaSuccess || cudaMalloc(&c->d_err, 4) != cudaSuccess) {
         g_gemm_err = "chain: cudaMalloc failed"; delete c; return nullptr;
     }
     cudaMemcpy(c->d_meta, meta.data(), n * sizeof(ChainMeta), cudaMemcpyHostToDevice);
-    cudaMemset(c->d_ready, 0, CH_MAX_PROB * CH_MAX_MB * 4);
+    cudaMemset(c->d_ready, 0, (CH_MAX_PROB * CH_MAX_MB + 32) * 4);
     cudaMemset(c->d_err, 0, 4);
     return c;
 }
@@ -885,9 +900,7 @@ void exb_chain_destroy(void* h) {
 }
 int exb_chain_launch(void* h, uint64_t stream) {
     Chain* c = (Chain*)h;
-    cudaError_t err = cudaMemsetAsync(c->d_ready, 0, CH_MAX_PROB * CH_MAX_MB * 4, (cudaStream_t)stream);
-    if (err == cudaSuccess)
-        err = exb::launch_pdl(exb_gemm_chain_kernel, dim3(c->grid), dim3(NUM_THREADS), c->smem, (cudaStream_t)stream,
+    cudaError_t err = exb::launch_pdl(exb_gemm_chain_kernel, dim3(c->grid), dim3(NUM_THREADS), c->smem, (cudaStream_t)stream,
                               c->maps, (const ChainMeta*)c->d_meta, c->nprob, c->total, c->d_ready, c->d_err);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { g_gemm_err = std::string("chain launch: ") + cudaGetErrorString(err); return -1; }
