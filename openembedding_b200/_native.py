@@ -133,6 +133,21 @@ def cuda():
         P(lib, "exb_pull_plan", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_int, c_uint64])
         P(lib, "exb_plan_memory", c_int, [c_void_p, u64p])
         P(lib, "exb_engine_status_ptr", c_uint64, [c_void_p])
+        P(lib, "exb_ds_last_error", c_char_p, [])
+        P(lib, "exb_ds_create", c_void_p, [c_int, c_int, c_int, c_uint64, c_int, c_int, c_int, c_uint64])
+        P(lib, "exb_ds_destroy", None, [c_void_p])
+        P(lib, "exb_ds_set_initializer", c_int, [c_void_p, c_int, c_double, c_double, c_double, c_uint64])
+        P(lib, "exb_ds_set_optimizer", c_int, [c_void_p, c_int, f64p, c_int])
+        P(lib, "exb_ds_state_dim", c_int, [c_void_p])
+        P(lib, "exb_ds_num_items", c_uint64, [c_void_p])
+        P(lib, "exb_ds_pull", c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64])
+        P(lib, "exb_ds_update", c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64])
+        P(lib, "exb_ds_get", c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64])
+        P(lib, "exb_ds_set", c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64])
+        P(lib, "exb_ds_enumerate", c_int, [c_void_p, c_uint64, u64p])
+        P(lib, "exb_ds_clear", c_int, [c_void_p])
+        P(lib, "exb_ds_status", c_int, [c_void_p])
+        P(lib, "exb_ds_bytes", c_uint64, [c_void_p])
         P(lib, "exb_tier_create", c_void_p, [c_void_p, c_int, c_uint64])
         P(lib, "exb_tier_destroy", None, [c_void_p])
         P(lib, "exb_tier_admit", c_int, [c_void_p, c_uint64, c_uint64, c_uint32, c_uint64])

@@ -733,7 +733,8 @@ class EmbeddingGroup:
         self.model = model
         self.ctx = get_context()
         self.layers = [l for _, l in _iter_embeddings(model)
-                       if not l.sparse_as_dense and getattr(l.variable, "tier", None) is None]
+                       if not l.sparse_as_dense and getattr(l.variable, "tier", None) is None
+                       and l.variable._tdtype == torch.float32]
         for l in self.layers:
             l._group = self
         self.state = "trace" if (self.layers and self.ctx.device.type == "cuda") else "off"

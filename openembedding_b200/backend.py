@@ -253,6 +253,155 @@ class _CpuGroup:
         self.b.update(list(dict.fromkeys(self.metas)))
 
 
+# ====================================================================== CUDA, float64 tables
+class _F64Tables:
+    """float64 variables on the GPU (``csrc/cuda/dev_shard.cu``): device-resident shards with the CPU oracle's four
+    verbs executed by kernels (bit-identical math), ids / rows / gradients routed between ranks with NCCL
+    ``all_to_all_single`` on device tensors -- the structure of ``CpuBackend`` with every buffer in HBM.
+    Reference: float and double tables are both registered (EmbeddingVariable.cpp:277-278)."""
+
+    def __init__(self, be):
+        self.be = be
+        self.lib = be.engine.lib
+        self.dev = be.device
+        self.pending = {}
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("dev shard %s: %s" % (what, self.lib.exb_ds_last_error().decode()))
+
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def create(self, meta):
+        be = self.be
+        my = (be.rank - meta.shard_base) % be.world
+        meta.my_shard = my if my < meta.shard_num else -1
+        cap = getattr(meta, "capacity", None) or (1 << 16)
+        h = self.lib.exb_ds_create(be.engine.device_index, 8, meta.dim, 0 if meta.is_hash else meta.vocab,
+                                   max(meta.my_shard, 0), meta.shard_num, 1 if meta.is_hash else 0, int(cap))
+        if not h:
+            raise RuntimeError("exb_ds_create: " + self.lib.exb_ds_last_error().decode())
+        meta.handle, meta.f64, meta.allocated = h, True, True
+        return meta
+
+    def set_initializer(self, meta, cfg):
+        kind, p, seed = initializer_params(cfg)
+        self._ck(self.lib.exb_ds_set_initializer(meta.handle, kind, p[0], p[1], p[2], mix_seed(seed, meta.variable_id)), "init")
+
+    def set_optimizer(self, meta, cfg):
+        kind, p = optimizer_params(cfg)
+        self._ck(self.lib.exb_ds_set_optimizer(meta.handle, kind, (ctypes.c_double * 8)(*p), 8), "optimizer")
+
+    # ---- exchange (device tensors, NCCL)
+    def _a2a(self, send, send_counts, width, dtype):
+        import torch.distributed as dist
+        ci = torch.tensor(send_counts, dtype=torch.int64, device=self.dev)
+        co = torch.empty(self.be.world, dtype=torch.int64, device=self.dev)
+        dist.all_to_all_single(co, ci, group=self.be.group)
+        rc = co.tolist()
+        recv = torch.empty((sum(rc),) + ((width,) if width else ()), dtype=dtype, device=self.dev)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=list(send_counts),
+                               group=self.be.group)
+        return recv, rc
+
+    def _a2a_known(self, send, sc, rc, width, dtype):
+        import torch.distributed as dist
+        recv = torch.empty((sum(rc),) + ((width,) if width else ()), dtype=dtype, device=self.dev)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=list(rc), input_split_sizes=list(sc),
+                               group=self.be.group)
+        return recv
+
+    def _pull_local(self, meta, local):
+        rows = torch.empty((local.numel(), meta.dim), dtype=torch.float64, device=self.dev)
+        self._ck(self.lib.exb_ds_pull(meta.handle, local.data_ptr(), local.numel(), rows.data_ptr(), self._st()), "pull")
+        return rows
+
+    def pull(self, meta, ids):
+        ids = ids.reshape(-1).to(device=self.dev, dtype=torch.int64).contiguous()
+        uniq, inverse = torch.unique(ids, return_inverse=True)
+        W = self.be.world
+        if W == 1:
+            return self._pull_local(meta, (uniq // meta.shard_num).contiguous())[inverse]
+        owner, local = _owner_local(uniq, meta, W)
+        order = torch.argsort(owner, stable=True)
+        sc = torch.bincount(owner, minlength=W).tolist()
+        req, rc = self._a2a(local[order], sc, 0, torch.int64)
+        rows = self._pull_local(meta, req.contiguous())
+        back = self._a2a_known(rows, rc, sc, meta.dim, torch.float64)
+        urows = torch.empty((uniq.numel(), meta.dim), dtype=torch.float64, device=self.dev)
+        urows[order] = back
+        return urows[inverse]
+
+    def push(self, meta, ids, grads):
+        ids = ids.reshape(-1).to(device=self.dev, dtype=torch.int64)
+        grads = grads.reshape(-1, meta.dim).to(device=self.dev, dtype=torch.float64)
+        self.pending.setdefault(meta.variable_id, []).append((ids, grads))
+
+    def update(self, meta):
+        pend = self.pending.pop(meta.variable_id, None)
+        W = self.be.world
+        if not pend:
+            if W == 1:
+                return
+            ids = torch.zeros(0, dtype=torch.int64, device=self.dev)
+            g = torch.zeros((0, meta.dim), dtype=torch.float64, device=self.dev)
+        else:
+            ids = torch.cat([p[0] for p in pend])
+            g = torch.cat([p[1] for p in pend])
+        # K4a: per-worker pre-reduce (sum duplicate gradients, count them)
+        uniq, inverse, counts = torch.unique(ids, return_inverse=True, return_counts=True)
+        gs = torch.zeros((uniq.numel(), meta.dim), dtype=torch.float64, device=self.dev).index_add_(0, inverse, g)
+        if W == 1:
+            local, cnt = (uniq // meta.shard_num).contiguous(), counts.contiguous()
+        else:
+            owner, loc = _owner_local(uniq, meta, W)
+            order = torch.argsort(owner, stable=True)
+            sc = torch.bincount(owner, minlength=W).tolist()
+            rid, rc = self._a2a(loc[order], sc, 0, torch.int64)
+            rg = self._a2a_known(gs[order], sc, rc, meta.dim, torch.float64)
+            rcnt = self._a2a_known(counts[order], sc, rc, 0, torch.int64)
+            local, inv2 = torch.unique(rid, return_inverse=True)          # K4b: combine the sources
+            gs = torch.zeros((local.numel(), meta.dim), dtype=torch.float64, device=self.dev).index_add_(0, inv2, rg)
+            cnt = torch.zeros(local.numel(), dtype=torch.int64, device=self.dev).index_add_(0, inv2, rcnt)
+        if local.numel():
+            self._ck(self.lib.exb_ds_update(meta.handle, local.data_ptr(), local.numel(), gs.data_ptr(), cnt.data_ptr(),
+                                            self._st()), "update")
+        torch.cuda.current_stream(self.dev).synchronize()      # keeps local / gs / cnt alive until the kernel ran
+        if self.lib.exb_ds_status(meta.handle):
+            from .status import Status, StatusError
+            raise StatusError(Status.OOM, "float64 shard full")
+
+    # ---- checkpoint side
+    def num_items(self, meta):
+        return int(self.lib.exb_ds_num_items(meta.handle))
+
+    def local_ids(self, meta):
+        n = self.num_items(meta)
+        out = torch.empty(max(n, 1), dtype=torch.int64, device=self.dev)
+        cnt = (ctypes.c_uint64 * 1)()
+        self._ck(self.lib.exb_ds_enumerate(meta.handle, out.data_ptr(), cnt), "enumerate")
+        return torch.sort(out[: int(cnt[0])])[0]
+
+    def get(self, meta, local, with_state=True):
+        local = local.to(device=self.dev, dtype=torch.int64).contiguous()
+        sd = int(self.lib.exb_ds_state_dim(meta.handle))
+        w = torch.empty((local.numel(), meta.dim), dtype=torch.float64, device=self.dev)
+        s = torch.empty((local.numel(), max(sd, 1)), dtype=torch.float64, device=self.dev)
+        self._ck(self.lib.exb_ds_get(meta.handle, local.data_ptr(), local.numel(), w.data_ptr(),
+                                     s.data_ptr() if (with_state and sd) else 0, self._st()), "get")
+        torch.cuda.current_stream(self.dev).synchronize()
+        return w, (s[:, :sd] if with_state else s[:, :0])
+
+    def set(self, meta, local, w, s):
+        local = local.to(device=self.dev, dtype=torch.int64).contiguous()
+        w = w.to(device=self.dev, dtype=torch.float64).contiguous()
+        s = s.to(device=self.dev, dtype=torch.float64).contiguous() if s is not None else None
+        self._ck(self.lib.exb_ds_set(meta.handle, local.data_ptr(), local.numel(), w.data_ptr(),
+                                     s.data_ptr() if s is not None else 0, self._st()), "set")
+        torch.cuda.current_stream(self.dev).synchronize()
+
+
 # ====================================================================== CUDA
 class CudaBackend:
     name = "cuda"
@@ -266,10 +415,17 @@ class CudaBackend:
         self._plans = {}      # (variable_id, B) -> SparsePlan
         self._pending = {}    # variable_id -> [(ids, grads)]
         self.hash_reserve = 1 << 20
+        self._f64 = None      # float64 tables (dev_shard.cu)
 
     def create_variable(self, meta):
+        if meta.dtype == "float64":          # exact fp64 shard engine (dev_shard.cu); fp32 = the fused engine
+            if self._f64 is None:
+                self._f64 = _F64Tables(self)
+            self._f64.create(meta)
+            self.vars.append(meta)
+            return meta
         if meta.dtype != "float32":
-            raise ValueError("the CUDA engine stores float32 tables (use flags.device='cpu' for float64)")
+            raise ValueError("unsupported dtype for server variable: %s" % meta.dtype)
         t = self.engine.add_table(meta.dim, meta.vocab, meta.is_hash,
                                   capacity=getattr(meta, "capacity", None) or self.hash_reserve,
                                   shard_num=meta.shard_num, shard_base=meta.shard_base)
@@ -279,6 +435,8 @@ class CudaBackend:
         return meta
 
     def set_initializer(self, meta, cfg):
+        if getattr(meta, "f64", False):
+            return self._f64.set_initializer(meta, cfg)
         if getattr(meta, "allocated", False):
             # weights are materialised eagerly; a later initializer only affects rows
             # that are (re)created from now on (hash misses, clear()).
@@ -286,6 +444,8 @@ class CudaBackend:
         self.engine.set_initializer(meta.handle, cfg, meta.variable_id)
 
     def set_optimizer(self, meta, cfg):
+        if getattr(meta, "f64", False):
+            return self._f64.set_optimizer(meta, cfg)
         self.engine.set_optimizer(meta.handle, cfg)
         if getattr(meta, "allocated", False):
             self.engine.commit()
@@ -297,7 +457,7 @@ class CudaBackend:
 
     def ensure_allocated(self, metas=None):
         """Collective: materialise not-yet-allocated tables and map them on every peer."""
-        todo = [m for m in (metas or self.vars) if not m.allocated]
+        todo = [m for m in (metas or self.vars) if not m.allocated and not getattr(m, "f64", False)]
         if not todo:
             return
         self._check_memory_limits(todo)
@@ -354,12 +514,16 @@ class CudaBackend:
         return plan
 
     def pull(self, meta, ids):
+        if getattr(meta, "f64", False):
+            return self._f64.pull(meta, ids)
         ids = ids.reshape(-1, 1).to(device=self.device, dtype=torch.int64).contiguous()
         plan = self._plan_for(meta, ids.shape[0])
         out = plan.pull(ids)
         return out[:, :meta.dim] if out.shape[1] != meta.dim else out
 
     def push(self, meta, ids, grads):
+        if getattr(meta, "f64", False):
+            return self._f64.push(meta, ids, grads)
         ids = ids.reshape(-1, 1).to(device=self.device, dtype=torch.int64).contiguous()
         grads = grads.reshape(-1, meta.dim).to(device=self.device, dtype=torch.float32)
         self._pending.setdefault(meta.variable_id, []).append((ids, grads))
@@ -369,6 +533,9 @@ class CudaBackend:
         variable some rank may have pushed to (n = 0 where this rank has nothing) -- a rank that skipped the
         launch would leave its peers waiting in the in-kernel barrier."""
         for meta in (metas or self.vars):
+            if getattr(meta, "f64", False):
+                self._f64.update(meta)
+                continue
             pend = self._pending.pop(meta.variable_id, None)
             if not pend:
                 if self.world == 1:
@@ -386,6 +553,8 @@ class CudaBackend:
             plan.push_update(ids, g.contiguous())
 
     def make_group(self, metas, batch, feat_cols=None, ncols=None):
+        if any(getattr(m, "f64", False) for m in metas):
+            raise ValueError("fused plans are float32; float64 variables use the per-variable path")
         self.ensure_allocated(list(metas))
         plan = self.engine.make_plan([m.handle for m in metas], batch, feat_cols=feat_cols, ncols=ncols)
         self.engine.connect(self.group)
@@ -393,6 +562,8 @@ class CudaBackend:
 
     # ---- checkpoint side
     def num_items(self, meta):
+        if getattr(meta, "f64", False):
+            return self._f64.num_items(meta) if meta.my_shard >= 0 else 0
         self.ensure_allocated([meta])
         if meta.is_hash:
             return self.engine.table_size(meta.handle)
@@ -410,6 +581,15 @@ class CudaBackend:
         blocks -- gather kernel into a device staging buffer, asynchronous D2H into one of two PINNED host buffers
         on a copy stream -- while the caller writes the previous chunk's blocks: the copy of chunk i+1 overlaps the
         file writes of chunk i. Yields (local indices, weights, states) per file block (views of the pinned buffer)."""
+        if getattr(meta, "f64", False):
+            if meta.my_shard < 0:
+                return
+            local = self._f64.local_ids(meta)
+            for i in range(0, local.numel(), block_rows):
+                blk = local[i:i + block_rows]
+                w, s = self._f64.get(meta, blk, with_state=with_state)
+                yield blk.cpu().numpy().astype(np.uint64), w.cpu().numpy(), s.cpu().numpy()
+            return
         self.ensure_allocated([meta])
         if self.shard_id(meta) < 0:
             return
@@ -469,6 +649,19 @@ class CudaBackend:
         return w.cpu().numpy(), (s.cpu().numpy() if (s is not None and sd) else np.empty((ids.numel(), 0), np.float32))
 
     def load_rows(self, meta, global_ids, weights, states):
+        if getattr(meta, "f64", False):
+            ids = np.asarray(global_ids, dtype=np.uint64)
+            owner = (meta.shard_base + (ids % np.uint64(meta.shard_num)).astype(np.int64)) % self.world
+            m = owner == self.rank
+            if not m.any():
+                return
+            sd = self.state_dim(meta)
+            st = np.asarray(states)
+            has_state = st.size > 0 and st.shape[1] == sd and sd > 0
+            self._f64.set(meta, torch.from_numpy((ids[m] // np.uint64(meta.shard_num)).astype(np.int64)),
+                          torch.from_numpy(np.ascontiguousarray(np.asarray(weights)[m], dtype=np.float64)),
+                          torch.from_numpy(np.ascontiguousarray(st[m], dtype=np.float64)) if has_state else None)
+            return
         self.ensure_allocated([meta])
         ids = np.asarray(global_ids, dtype=np.uint64)
         owner = (meta.shard_base + (ids % np.uint64(meta.shard_num)).astype(np.int64)) % self.world
@@ -483,8 +676,14 @@ class CudaBackend:
                                  torch.from_numpy(np.ascontiguousarray(st[m], dtype=np.float32)) if has_state else None)
 
     def clear(self, meta):
+        if getattr(meta, "f64", False):
+            self.lib_ds_clear(meta)
+            return
         if meta.allocated:
             self.engine.clear_table(meta.handle)
+
+    def lib_ds_clear(self, meta):
+        self._f64._ck(self._f64.lib.exb_ds_clear(meta.handle), "clear")
 
     def table_kind(self, meta):
         return "hash" if meta.is_hash else "array"
@@ -538,4 +737,9 @@ class CudaBackend:
         torch.cuda.synchronize(self.device)
 
     def close(self):
+        if self._f64 is not None:
+            for m in self.vars:
+                if getattr(m, "f64", False) and m.handle:
+                    self._f64.lib.exb_ds_destroy(m.handle)
+                    m.handle = None
         self.engine.close()
