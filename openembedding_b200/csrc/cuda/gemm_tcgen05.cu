@@ -53,7 +53,7 @@ struct GemmEpi {
     __nv_bfloat16* outT; long long ldoT;
     const __nv_bfloat16* mask; long long ldmask;
     const float* dlogit; const float* S; const float* emb; long long ldemb;
-    int swap, _pad2;
+    int swap, mc;              // mc: CTAs per cluster along the N-tile axis that share (multicast) the A tile; <= 1: off
     unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) [start, setup, first-full, mainloop, epilogue]
 };
 
@@ -108,6 +108,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// A-tile multicast: the tile lands at the same shared-memory offset of every CTA in `mask` and completes the
+// transaction bytes on each destination CTA's own barrier (same offset)
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// commit that arrives on the barrier at the same offset in every CTA of `mask` (stage released cluster-wide)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -153,9 +168,17 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int kb0 = blockIdx.z * k_blocks_per_split;
     const int kb1 = min(num_k_blocks, kb0 + k_blocks_per_split);
     const int nkb = kb1 - kb0;
+    // E.mc > 1: launched as clusters of E.mc CTAs with the same M block and consecutive N blocks. Rank 0 loads the A
+    // tile ONCE and multicasts it into every CTA of the cluster (A is 2/3 of the operand bytes of a 128x64 tile and
+    // the GEMMs of the step are bound by operand traffic out of L2); each CTA loads its own B tile. A stage is
+    // re-filled only when EVERY CTA of the cluster has consumed it: the MMA commits arrive on all CTAs' barriers.
+    const int C = E.mc > 1 ? E.mc : 1;
+    uint32_t crank = 0;
+    if (C > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const uint16_t cmask = (uint16_t)((1u << C) - 1u);
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)C); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -169,6 +192,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (C > 1) cluster_sync_all();     // every CTA's barriers exist before a peer multicasts into / arrives on them
     exb::pdl_wait();      // barriers, TMEM and tensor maps are ready; operands come from the previous kernel
     if (threadIdx.x == 0) GSTAMP(1);
 
@@ -180,14 +204,25 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                 if (E.mn_major) {   // boxes of 64 MN elements x 64 k rows; the A tile is two MN blocks
-                    tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], m_blk * BM, (kb0 + i) * BK);
-                    tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], m_blk * BM + 64, (kb0 + i) * BK);
+                    if (C > 1) {
+                        if (crank == 0) {
+                            tma_load_2d_mc(sA + s * A_BYTES, &tmA, &full[s], m_blk * BM, (kb0 + i) * BK, cmask);
+                            tma_load_2d_mc(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], m_blk * BM + 64, (kb0 + i) * BK, cmask);
+                        }
+                    } else {
+                        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], m_blk * BM, (kb0 + i) * BK);
+                        tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], m_blk * BM + 64, (kb0 + i) * BK);
+                    }
 #pragma unroll
                     for (int h = 0; h < BN / 64; ++h)
                         tma_load_2d(sB + s * B_BYTES + h * 8192, &tmB, &full[s], n_blk * BN + 64 * h, (kb0 + i) * BK);
                     continue;
                 }
-                tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + i) * BK, m_blk * BM);
+                if (C > 1) {
+                    if (crank == 0) tma_load_2d_mc(sA + s * A_BYTES, &tmA, &full[s], (kb0 + i) * BK, m_blk * BM, cmask);
+                } else {
+                    tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + i) * BK, m_blk * BM);
+                }
                 tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], (kb0 + i) * BK, n_blk * BN);
             }
         }
@@ -214,7 +249,8 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128B swizzle row
                     umma_bf16(tmem_base, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc, (i | k) ? 1u : 0u);
                 }
-                umma_commit(&empty[s]);            // smem stage reusable when these MMAs retire
+                if (C > 1) umma_commit_mc(&empty[s], cmask);   // the stage is free once EVERY CTA of the cluster has read it
+                else umma_commit(&empty[s]);       // smem stage reusable when these MMAs retire
             }
             umma_commit(tmem_full);                // accumulator complete
         }
@@ -346,6 +382,7 @@ exb_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
     __syncthreads();
     if (threadIdx.x == 0) GSTAMP(5);
+    if (C > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into / arrive on its memory
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -719,8 +756,33 @@ cudaError_t launch_gemm(dim3 grid, cudaStream_t stream, const CUtensorMap& tmA, 
         cudaFuncSetAttribute(exb_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
         attr_set = true;
     }
+    if (E.mc > 1) {       // clusters of E.mc CTAs along grid.y (the N-tile axis when swap == 0)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = gemm_smem<BN>(); cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)E.mc; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = exb::pdl_enabled() ? 2 : 1;
+        return cudaLaunchKernelEx(&cfg, exb_gemm_tcgen05_kernel<BN>, tmA, tmB, tmO, tmT, E, nkb, per);
+    }
     return exb::launch_pdl(exb_gemm_tcgen05_kernel<BN>, grid, dim3(NUM_THREADS), gemm_smem<BN>(), stream, tmA, tmB, tmO, tmT,
                            E, nkb, per);
+}
+
+// cluster size for the A-tile multicast: the largest divisor (<= EXB_GEMM_MC, <= 8) of the number of N tiles.
+// OFF by default (EXB_GEMM_MC unset / 0): measured on B200 the lock-step clusters cost more than the 2.3x smaller
+// L2 read traffic buys for this step's shapes (fwd 32.8 -> 37.8 us, dX 54 -> 67 us; profiles/r2/dense_path.md) --
+// the main loop is bound by TMA round-trip latency per ring slot, not by L2 bandwidth.
+int pick_mc(int n_tiles) {
+    static int lim = -1;
+    if (lim < 0) { const char* e = getenv("EXB_GEMM_MC"); lim = e ? atoi(e) : 0; }
+    if (lim <= 1 || pick_swap()) return 1;
+    int best = 1;
+    for (int c = 2; c <= 8 && c <= lim; ++c)
+        if (n_tiles % c == 0) best = c;
+    return best;
 }
 
 }  // namespace
@@ -761,7 +823,7 @@ int exb_gemm_bf16_nt(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    E.swap = pick_swap(); E._pad2 = 0;
+    E.swap = pick_swap(); E.mc = pick_mc((int)grid.y);
     if (E.swap) grid = dim3(grid.y, grid.x, grid.z);
     cudaError_t err = BN == 128 ? launch_gemm<128>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per)
                                 : launch_gemm<64>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
@@ -793,7 +855,7 @@ int exb_gemm_bf16_tn(uint64_t A, long long lda, uint64_t B, long long ldb, int M
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-    E.swap = pick_swap(); E._pad2 = 0;
+    E.swap = pick_swap(); E.mc = pick_mc((int)grid.y);
     if (E.swap) grid = dim3(grid.y, grid.x, grid.z);
     cudaError_t err = BN == 128 ? launch_gemm<128>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per)
                                 : launch_gemm<64>(grid, (cudaStream_t)stream, tmA, tmB, tmO, tmT, E, nkb, per);
@@ -841,7 +903,7 @@ void* exb_chain_create(const void* descs, int n, int sms) {
         E.out = (void*)d.out; E.ldo = d.ldo; E.outT = nullptr; E.ldoT = 0;
         E.mask = (const __nv_bfloat16*)d.mask; E.ldmask = d.ldmask;
         E.dlogit = (const float*)d.dlogit; E.S = (const float*)d.S; E.emb = (const float*)d.emb; E.ldemb = d.ldemb;
-        E.swap = 0; E._pad2 = 0; E.dbg = nullptr;
+        E.swap = 0; E.mc = 1; E.dbg = nullptr;
         const bool f32out = (E.mode == EPI_DW || E.mode == EPI_DX_FM);
         bool ok;
         if (d.tn) {

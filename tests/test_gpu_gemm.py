@@ -176,3 +176,27 @@ def test_tc_linear_matches_torch(M, K, N):
     close(x2.grad, x1.grad, "dx")
     close(tc.weight.grad, ref.weight.grad, "dw")
     close(tc.bias.grad, ref.bias.grad, "db")
+
+
+def test_cluster_multicast_variant_matches(monkeypatch):
+    """EXB_GEMM_MC: the A tile is loaded once per cluster and multicast into the CTAs that share it"""
+    import subprocess, sys, os
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from openembedding_b200.ops.gemm import EPI_FWD, gemm_nt, gemm_tn\n"
+        "g = torch.Generator(device='cuda').manual_seed(0)\n"
+        "A = (torch.randn(1024, 448, device='cuda', generator=g)).to(torch.bfloat16)\n"
+        "B = (torch.randn(448, 448, device='cuda', generator=g) * 0.1).to(torch.bfloat16)\n"
+        "out = torch.zeros(1024, 448, device='cuda', dtype=torch.bfloat16)\n"
+        "gemm_nt(A, B, 1024, 448, 448, out, mode=EPI_FWD, relu=True, ones_col=447)\n"
+        "gw = torch.zeros(448, 448, device='cuda')\n"
+        "gemm_tn(A, A, 448, 448, 1024, gw, splits=4)\n"
+        "torch.cuda.synchronize()\n"
+        "ref = torch.relu(A.float() @ B.float().t()); ref[:, 447] = 1\n"
+        "assert torch.allclose(out.float(), ref, atol=3e-2, rtol=3e-2), float((out.float() - ref).abs().max())\n"
+        "refw = A.float().t() @ A.float()\n"
+        "assert torch.allclose(gw, refw, atol=0.5, rtol=2e-2), float((gw - refw).abs().max())\n"
+        "print('MC_OK')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, EXB_GEMM_MC="8"), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert "MC_OK" in r.stdout, r.stdout[-2000:]
