@@ -47,9 +47,9 @@ def parse():
     p.add_argument("--allreduce", default="auto")
     p.add_argument("--skew", type=float, default=1.0, help="0 = uniform ids, 1 = log-uniform (Zipf-like)")
     p.add_argument("--pool", type=int, default=16, help="distinct pre-generated batches cycled through")
-    p.add_argument("--prefetch", action="store_true",
-                   help="announce the next batch's ids one step ahead (plan prefetch on a side stream, the reference's pulling()); "
-                        "measured slower than planning inside the pull launch, hence off by default")
+    p.add_argument("--no-prefetch", action="store_true",
+                   help="do not announce the next batch's ids one step ahead (default: the public prefetch API, the reference's "
+                        "pulling(): the next batch's pull + plan run beside this step's dense all-reduce / optimizer)")
     return p.parse_args()
 
 
@@ -239,7 +239,7 @@ def main():
         model = FusedCTR(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
                          sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
         trainer = FusedTrainer(model, use_graph=not a.no_graph)
-        trainer.want_prefetch = bool(a.prefetch)
+        trainer.want_prefetch = not a.no_prefetch
     else:
         model = CTRModel(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
                          sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
@@ -254,7 +254,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    prefetch = engine == "fused" and a.prefetch
+    prefetch = engine == "fused" and not a.no_prefetch
 
     def run_step(k):
         if prefetch:      # public prefetch API: the ids of the NEXT batch are announced one step ahead (reference: pulling())

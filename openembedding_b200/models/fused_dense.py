@@ -299,11 +299,13 @@ class FusedCTR:
                                           self.WTb[l].data_ptr(), self.Hp[l], dims[l], self._st()), "refresh_bf16")
 
     # ---- one training step (all launches on the current stream)
-    def forward_backward(self, ids, dense, labels, update=True, next_ids=None, planned=False):
-        """``next_ids``: ids of the NEXT batch (device tensor that stays unchanged until that batch has been
-        trained) -- its de-duplication plan is built on a side stream while this batch computes (prefetch, the
-        reference's ``pulling``). ``planned``: the caller guarantees that the current batch slot already holds the
-        plan of ``ids`` (CUDA-graph replays, where the python bookkeeping of the plan is bypassed)."""
+    def forward_backward(self, ids, dense, labels, update=True, next_ids=None, pulled=False):
+        """One training step. ``next_ids``: ids of the NEXT batch (a device tensor that stays unchanged until that
+        batch has been trained): after this batch's push+update the rows AND the de-duplication plan of the next
+        batch are pulled on a side stream, next to the dense all-reduce / optimizer of this step -- the prefetch of
+        the reference's ``pulling`` (exb.py:645-691; parked pulls, EmbeddingPullOperator.cpp:117-145: a pull of batch
+        k+1 may only see the tables after update k, which the stream order guarantees). ``pulled=True``: the caller
+        passes the batch that the previous step prefetched this way: X32 and the plan are ready, no pull up front."""
         B, L, lib, st = self.B, len(self.hidden), self.lib, self._st()
         assert ids.shape == (B, self.nf) and ids.dtype == torch.int64 and ids.is_contiguous()
         if self._grad_dirty:          # the optimizer kernel clears the gradients it consumed; a call with
@@ -312,19 +314,10 @@ class FusedCTR:
         self._mark("start")
         g = self.group
         v2 = getattr(g, "v2", False) and update
-        side_used = False
-        if v2:
-            if planned:
-                g._armed[0] = (g._key(ids), "prefetch")
-            if next_ids is not None:
-                cur = torch.cuda.current_stream(self.dev)
-                self._ev_fork.record(cur)
-                self._s2.wait_event(self._ev_fork)
-                g.prepare(next_ids, next=True, stream=self._s2.cuda_stream)
-                self._ev_plan.record(self._s2)
-                side_used = True
-            # training pull: gather + plan of this batch in one launch (or a plain gather if the plan was prefetched)
-            g.pull(ids, out=self.X32, train=True)
+        if pulled and v2:
+            g._armed[0] = (g._key(ids), "pull")        # rows + plan of this batch came with the previous step's tail
+        elif v2:
+            g.pull(ids, out=self.X32, train=True)      # gather + plan of the batch in one launch
         else:
             g.pull(ids, out=self.X32)
         self._mark("pull")
@@ -365,8 +358,6 @@ class FusedCTR:
             G.gemm_nt(self.dZ[0], self.WTb[0], B, self.K0p, self.Hp[0], self.G32, mode=G.EPI_DX_FM, dlogit=self.dlogit,
                       S=self.S, emb=self.X32, fm_cols=self.nf * self.Dp if self.use_fm else 0, D=self.Dp, stream=st)
         self._mark("dx_gemm")
-        if side_used:        # the plan(s) built on the side stream are complete before the push reads / flips the slots
-            torch.cuda.current_stream(self.dev).wait_event(self._ev_plan)
         forked = update and self.overlap
         if forked:
             cur = torch.cuda.current_stream(self.dev)
@@ -390,10 +381,19 @@ class FusedCTR:
                                   self.gview("cache_lin").data_ptr() if row_head else 0,
                                   self.cache_vocab.data_ptr(), st), "cachegrad")
         self._mark("dw_gemm+cachegrad")
+        tail = False
         if update:
             if not forked:
                 self.group.push_update(ids, self.G32)
                 self._mark("push_update")
+            tail = next_ids is not None and v2 and not forked
+            if tail:      # next batch: rows into X32 (free since the dX1 GEMM) + plan, beside the dense optimizer
+                cur = torch.cuda.current_stream(self.dev)
+                self._ev_fork.record(cur)
+                self._s2.wait_event(self._ev_fork)
+                with torch.cuda.stream(self._s2):
+                    g.pull(next_ids, out=self.X32, train=True)
+                    self._ev_plan.record(self._s2)
             # Adagrad + bf16 weight refresh + gradient clearing: one kernel (world > 1: behind the all-reduce,
             # in the same kernel)
             # world > 1: the all-reduce runs on one CTA per SM (every CTA polls peer flags); the optimizer kernel
@@ -406,6 +406,9 @@ class FusedCTR:
             if forked:
                 torch.cuda.current_stream(self.dev).wait_event(self._ev_join)
                 self._mark("join(push_update)")
+            if tail:
+                torch.cuda.current_stream(self.dev).wait_event(self._ev_plan)
+                self._mark("join(prefetch pull)")
         else:
             self._grad_dirty = True
         return self.loss.view(())
@@ -473,75 +476,87 @@ class FusedTrainer:
     stream -- the prefetch of the reference's ``pulling`` (exb.py:645-691)."""
 
     supports_prefetch = True
-    want_prefetch = False        # set True to let ``make_pipeline`` run one batch ahead and prefetch the plans
+    want_prefetch = True         # ``make_pipeline`` runs one batch ahead: the next batch's pull overlaps this step's tail
 
     def __init__(self, model, use_graph=True):
         self.m, self.ctx = model, model.ctx
         self.device, self.world = model.dev, model.ctx.world
         self.use_graph = use_graph
-        self.graph, self._static = None, None
+        self._graphs, self._static = {}, None      # (pull up front?, prefetch pull at the tail?) -> CUDAGraph
+        self.graph = None
         self._ar = model._ar
-        self.prefetch = False            # decided at capture time: was the first step given next_ids?
-        self._planned_key = None         # key of the batch whose plan the last step prefetched
+        self._x32_key = None         # key of the batch whose rows + plan the last step prefetched into X32
+        self._warm = False
 
     def step(self, ids, dense, labels, next_ids=None):
         g = self.m.group
         v2 = getattr(g, "v2", False)
         if not v2:
             next_ids = None
+        pulled = v2 and self._x32_key is not None and self._x32_key == g._key(ids)
+        tail = next_ids is not None
         if not self.use_graph:
-            loss = self.m.forward_backward(ids, dense, labels, next_ids=next_ids)
+            if not pulled and self._x32_key is not None:
+                g.reset_slot(0)                     # a prefetched batch that is not the one trained now
+            loss = self.m.forward_backward(ids, dense, labels, next_ids=next_ids, pulled=pulled)
+            self._x32_key = g._key(next_ids) if tail else None
             self.ctx.step_done()
             return loss
-        if self.graph is None:
-            self._capture(ids, dense, labels, next_ids)
+        if self._static is None:
+            self._static = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone(), "next_ids": ids.clone()}
         s = self._static
         if ids.data_ptr() != s["ids"].data_ptr():
             s["ids"].copy_(ids, non_blocking=True)
             s["dense"].copy_(dense, non_blocking=True)
             s["labels"].copy_(labels, non_blocking=True)
-        if self.prefetch:
-            if self._planned_key is None or self._planned_key != g._key(ids):
-                # the current slot does not hold the plan of this batch (first step, or the caller changed its
-                # mind about the next batch): plan it now, eagerly
-                g.prepare(s["ids"], next=False)
-            if next_ids is not None:
-                s["next_ids"].copy_(next_ids, non_blocking=True)
-                self._planned_key = g._key(next_ids)
-            else:
-                self._planned_key = None     # the graph still plans the stale static batch; it is dropped next step
-        self.graph.replay()
+        if tail:
+            s["next_ids"].copy_(next_ids, non_blocking=True)
+        if not pulled and self._x32_key is not None:
+            g.reset_slot(0)                         # drop the prefetched plan: this is a different batch
+        key = (not pulled, tail)
+        gr = self._graphs.get(key)
+        if gr is None:
+            gr = self._capture(key)
+        gr.replay()
+        # replays bypass the plan's python bookkeeping: if a batch was prefetched the current slot is armed on the
+        # device under a key no tensor can match -- any eager use of the plan re-plans
         if v2:
-            # replays bypass the plan's python bookkeeping: after the push the current slot holds what the graph
-            # planned as "next" (if anything) under a key no tensor can match -> any eager use re-plans
-            g._armed = [(("graph", id(self)), "pull") if self.prefetch else None, None]
+            g._armed = [(("graph", id(self)), "pull") if tail else None, None]
+        self._x32_key = g._key(next_ids) if tail else None
+        self.graph = gr
         self.ctx.step_done()
         return s["loss"]
 
-    def _capture(self, ids, dense, labels, next_ids=None):
-        s = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone()}
-        g = self.m.group
-        self.prefetch = next_ids is not None and getattr(g, "v2", False)
-        if self.prefetch:
-            s["next_ids"] = next_ids.clone()
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self.m.forward_backward(s["ids"], s["dense"], s["labels"])
-        torch.cuda.current_stream(self.device).wait_stream(side)
+    def _capture(self, key):
+        head, tail = key
+        s, g = self._static, self.m.group
+        if not self._warm:          # allocator / lazy init warm-up, outside any capture
+            assert head, "the first step of a trainer always pulls up front"
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                self.ctx.barrier()
+            self._warm = True
         torch.cuda.synchronize(self.device)
-        if self.world > 1:
-            self.ctx.barrier()
+        saved = list(getattr(g, "_armed", [None, None]))
+        if getattr(g, "v2", False):
+            g._armed = [None, None]
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
-            if self.prefetch:
-                s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"], next_ids=s["next_ids"], planned=True)
-            else:
-                s["loss"] = self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+            loss = self.m.forward_backward(s["ids"], s["dense"], s["labels"], next_ids=s["next_ids"] if tail else None,
+                                           pulled=not head)
+        s.setdefault("loss", loss)
+        if loss.data_ptr() != s["loss"].data_ptr():
+            s["loss"] = loss
         if getattr(g, "v2", False):
-            g._armed = [None, None]      # capture only recorded launches: no slot is armed on the device
-        self.graph, self._static = gr, s
+            g._armed = saved            # capture only recorded launches: the device-side slots are untouched
+        self._graphs[key] = gr
+        return gr
 
     def make_pipeline(self, batch, num_sparse, num_dense):
         from .trainer import _Pipeline

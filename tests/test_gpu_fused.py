@@ -64,3 +64,35 @@ def test_fused_trains_and_graph(cuda_context):
     losses = [float(tr.step(*b)) for _ in range(10)]
     ctx.backend.engine.check()
     assert losses[-1] < losses[0] - 0.01, losses
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_prefetch_next_batch_matches_plain(cuda_context, graph):
+    """step(..., next_ids=) pulls the next batch's rows + plan beside this step's dense optimizer (the reference's
+    pulling()); the training trajectory is the one of plain steps. Includes a break in the announced sequence."""
+    from openembedding_b200.context import get_context, reset_context
+    from openembedding_b200.models.fused_dense import FusedCTR, FusedTrainer
+    vocab = [1000, 50, 20000, 7, 3000] + [300] * 21
+    B = 256
+    curves = []
+    for prefetch in (False, True):
+        reset_context()
+        ctx = get_context()
+        m = FusedCTR(vocab, embedding_dim=16, model="deepfm", batch=B, cache_threshold=64, lr=0.05,
+                     sparse_optimizer={"category": "adagrad", "learning_rate": 0.05})
+        tr = FusedTrainer(m, use_graph=graph)
+        batches = [_batch(vocab, B, ctx.device, seed=s) for s in range(4)]
+        order = [0, 1, 2, 3, 0, 2, 1, 3, 3, 0]
+        losses = []
+        for k, i in enumerate(order):
+            nxt = None
+            if prefetch and k + 1 < len(order) and k != 4:        # k == 4: no announcement -> next step pulls up front
+                nxt = batches[order[k + 1]][0]
+            if prefetch and k == 6:                               # announce one batch, train another: plan is dropped
+                nxt = batches[0][0]
+            losses.append(float(tr.step(*batches[i], next_ids=nxt)))
+        torch.cuda.synchronize()
+        ctx.backend.engine.check()
+        curves.append(losses)
+    for a, b in zip(*curves):
+        assert abs(a - b) < 2e-4, curves
