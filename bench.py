@@ -39,7 +39,8 @@ def parse():
     p.add_argument("--dim", type=int, default=64)
     p.add_argument("--batch", type=int, default=4096, help="per-GPU batch (weak scaling)")
     p.add_argument("--vocab", default="criteo1tb_20m", choices=["criteo1tb_20m", "kaggle", "tiny"])
-    p.add_argument("--optimizer", default="adagrad")
+    p.add_argument("--optimizer", default="adagrad", help="sparse AND dense optimizer (adagrad | adam | ftrl, like the reference "
+                   "benchmark's --optimizer); other sparse optimizers keep Adagrad on the dense side")
     p.add_argument("--cache", type=int, default=4096, help="replicate tables smaller than this (reference --cache)")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--engine", default="auto", choices=["auto", "fused", "eager"],
@@ -234,16 +235,17 @@ def main():
     engine = a.engine
     if engine == "auto":
         engine = "fused" if (a.model in ("deepfm", "wdl") and a.batch % 128 == 0) else "eager"
+    dense_opt = {"category": a.optimizer if a.optimizer in ("adagrad", "adam", "ftrl") else "adagrad"}
     if engine == "fused":
         from openembedding_b200.models.fused_dense import FusedCTR, FusedTrainer
         model = FusedCTR(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
-                         sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
+                         sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache, dense_optimizer=dense_opt)
         trainer = FusedTrainer(model, use_graph=not a.no_graph)
         trainer.want_prefetch = not a.no_prefetch
     else:
         model = CTRModel(vocab, num_dense=13, embedding_dim=a.dim, model=a.model, batch=a.batch,
                          sparse_optimizer={"category": a.optimizer}, cache_threshold=a.cache)
-        trainer = Trainer(model, use_graph=not a.no_graph, allreduce=a.allreduce)
+        trainer = Trainer(model, use_graph=not a.no_graph, allreduce=a.allreduce, dense_optimizer=dense_opt)
     dev = ctx.device
     host = make_batches(torch, vocab, 13, a.batch, a.pool, a.skew, 1000 + rank, dev)
     devb = [(i.to(dev), d.to(dev), l.to(dev)) for i, d, l in host]
@@ -323,7 +325,7 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / (pub * 1e3)) if pub else None,
             "dtype": "bf16", "data": "synthetic (Criteo-shaped: 26 sparse log-uniform ids + 13 dense, random-init weights)",
-            "config": {"model": "%s (DeepCTR architecture), emb dim %d, %s sparse / Adagrad dense" % (a.model, a.dim, a.optimizer),
+            "config": {"model": "%s (DeepCTR architecture), emb dim %d, %s sparse / %s dense" % (a.model, a.dim, a.optimizer, dense_opt["category"]),
                        "global_batch": gb, "seq_len": 1, "parallelism": "dp%d + row-sharded embeddings (id %% %d) over NVLink" % (world, world),
                        "vocab_rows_total": rows, "tables_fp32_gb": round(rows * (a.dim + 1) * 4 * 2 / 2 ** 30, 1),
                        "cache_threshold": a.cache, "cuda_graph": not a.no_graph, "engine": engine, "prefetch": prefetch,

@@ -35,6 +35,7 @@ struct PrepArgs {
     float* S; float* base;               // [B, Dp], [B]
     int B, K0p, Dp, nf, ns, lin0, use_fm;   // lin0 = first column of the server linear terms in X32
     float* loss;                         // [1] step loss accumulator, cleared here (head A adds to it)
+    int* opt_step;                       // [1] dense-optimizer step counter (Adam bias correction), advanced here
 };
 
 // prep A: grid (B/32, ceil(K0p/256)); thread t owns ONE column of 32 batch rows: gathers cached
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) exb_prep_b_kernel(PrepArgs a) {
     __shared__ float sq[8], sfm[8], sl[8];
     const int b0 = blockIdx.x * 8;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss) *a.loss = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.opt_step) *a.opt_step += 1;
     if (threadIdx.x < 8) { sq[threadIdx.x] = 0.f; sfm[threadIdx.x] = 0.f; sl[threadIdx.x] = 0.f; }
     __syncthreads();
     const int q4 = a.Dp / 4;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256) exb_prep_row_kernel(PrepArgs a) {
     exb::pdl_trigger();
     exb::pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss) *a.loss = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.opt_step) *a.opt_step += 1;
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= a.B) return;
@@ -530,7 +533,52 @@ struct DenseOptArgs {
     float lr, eps;
     int nmat, zero_grad;
     OptMat mat[4];
+    // optimizer of the dense parameters (tf.keras semantics, the ones the reference benchmark sweeps:
+    // test/benchmark/criteo_deepctr.py --optimizer Adagrad | Adam | Ftrl): 0 adagrad, 1 adam, 2 ftrl
+    int kind, _pad;
+    float* accum2;                 // second state slot (adam: v, ftrl: linear); accum = adam m / ftrl accumulator
+    const int* step;               // device step counter (adam bias correction)
+    float b1, b2;                  // adam
+    float l1, l2, l2s, lrp, beta;  // ftrl: l1, l2, l2 shrinkage, learning_rate_power, beta
+    float c1, c2;                  // adam: bias-corrected step size factors are computed per launch from *step
 };
+
+struct OptRun { int kind; float lr, eps, b1, b2, lr_t, l1, l2s, lrp, adj_l2; };
+
+__device__ __forceinline__ OptRun opt_run(const DenseOptArgs& o) {
+    OptRun r;
+    r.kind = o.kind; r.lr = o.lr; r.eps = o.eps; r.b1 = o.b1; r.b2 = o.b2; r.l1 = o.l1; r.l2s = o.l2s; r.lrp = o.lrp;
+    r.adj_l2 = o.l2 + o.beta / o.lr * 0.5f;
+    r.lr_t = o.lr;
+    if (o.kind == 1) {
+        const float t = (float)(o.step ? *o.step : 1);
+        r.lr_t = o.lr * sqrtf(1.f - powf(o.b2, t)) / (1.f - powf(o.b1, t));
+    }
+    return r;
+}
+
+// one parameter: w, state slots a (accum / m / ftrl accumulator) and b (adam v / ftrl linear)
+__device__ __forceinline__ void dense_opt_one(const OptRun& r, float& w, float& a, float& b, float g) {
+    if (r.kind == 0) {                       // adagrad: a += g^2; w -= lr g / (sqrt(a) + eps)
+        a += g * g;
+        float q;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(q) : "f"(a));      // 1 ulp; the IEEE sequences made this kernel issue bound
+        w -= __fdividef(r.lr * g, q + r.eps);
+    } else if (r.kind == 1) {                // adam (keras): m, v moments; w -= lr_t m / (sqrt(v) + eps)
+        a = r.b1 * a + (1.f - r.b1) * g;
+        b = r.b2 * b + (1.f - r.b2) * g * g;
+        w -= r.lr_t * a / (sqrtf(b) + r.eps);
+    } else {                                 // ftrl (keras / EmbeddingOptimizer.h:230-293)
+        const float gs = g + 2.f * r.l2s * w;
+        const float an = a + g * g;
+        const float pa = powf(an, -r.lrp), po = powf(a, -r.lrp);
+        b += gs - (pa - po) / r.lr * w;
+        a = an;
+        const float quad = pa / r.lr + 2.f * r.adj_l2;
+        const float l1a = fminf(fmaxf(b, -r.l1), r.l1);
+        w = (l1a - b) / quad;
+    }
+}
 
 __device__ __forceinline__ float adagrad_one(float& w, float& a, float g, float lr, float eps) {
     a += g * g;
@@ -542,6 +590,8 @@ __device__ __forceinline__ float adagrad_one(float& w, float& a, float g, float 
 
 __device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*tile)[33]) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // launched with 256 threads
+    const OptRun R = opt_run(o);
+    const bool two = o.kind != 0 && o.accum2 != nullptr;
     int tile_base = 0;
     for (int mi = 0; mi < o.nmat; ++mi) {
         const OptMat M = o.mat[mi];
@@ -550,14 +600,15 @@ __device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*ti
         const int G = (int)gridDim.x;
         for (int t = ((int)blockIdx.x - tile_base % G + G) % G; t < nt; t += G) {
             const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
-            float g4[4], a4[4], w4[4];
+            float g4[4], a4[4], w4[4], b4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {          // 12 independent loads in flight per thread
                 const int r = r0 + ty + 8 * u, c = c0 + tx;
-                g4[u] = a4[u] = w4[u] = 0.f;
+                g4[u] = a4[u] = w4[u] = b4[u] = 0.f;
                 if (r < M.R && c < M.C) {
                     const long long k = M.off + (long long)r * M.C + c;
                     g4[u] = __ldcg(o.grad + k); a4[u] = o.accum[k]; w4[u] = o.theta[k];
+                    if (two) b4[u] = o.accum2[k];
                 }
             }
 #pragma unroll
@@ -565,8 +616,9 @@ __device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*ti
                 const int i = ty + 8 * u, r = r0 + i, c = c0 + tx;
                 if (r < M.R && c < M.C) {
                     const long long k = M.off + (long long)r * M.C + c;
-                    adagrad_one(w4[u], a4[u], g4[u], o.lr, o.eps);
+                    dense_opt_one(R, w4[u], a4[u], b4[u], g4[u]);
                     o.accum[k] = a4[u];
+                    if (two) o.accum2[k] = b4[u];
                     o.theta[k] = w4[u];
                     if (o.zero_grad) o.grad[k] = 0.f;
                     M.Wb[(size_t)r * M.C + c] = __float2bfloat16_rn(w4[u]);
@@ -588,16 +640,20 @@ __device__ __forceinline__ void dense_opt_step(const DenseOptArgs& o, float (*ti
             const float4 g = __ldcg(reinterpret_cast<const float4*>(o.grad + i));
             float4 a = *reinterpret_cast<float4*>(o.accum + i);
             float4 w = *reinterpret_cast<float4*>(o.theta + i);
-            adagrad_one(w.x, a.x, g.x, o.lr, o.eps); adagrad_one(w.y, a.y, g.y, o.lr, o.eps);
-            adagrad_one(w.z, a.z, g.z, o.lr, o.eps); adagrad_one(w.w, a.w, g.w, o.lr, o.eps);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (two) b = *reinterpret_cast<float4*>(o.accum2 + i);
+            dense_opt_one(R, w.x, a.x, b.x, g.x); dense_opt_one(R, w.y, a.y, b.y, g.y);
+            dense_opt_one(R, w.z, a.z, b.z, g.z); dense_opt_one(R, w.w, a.w, b.w, g.w);
             *reinterpret_cast<float4*>(o.accum + i) = a;
+            if (two) *reinterpret_cast<float4*>(o.accum2 + i) = b;
             *reinterpret_cast<float4*>(o.theta + i) = w;
             if (o.zero_grad) *reinterpret_cast<float4*>(o.grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             for (long long k = i; k < o.n; ++k) {
-                float a = o.accum[k], w = o.theta[k];
-                adagrad_one(w, a, o.grad[k], o.lr, o.eps);
+                float a = o.accum[k], w = o.theta[k], b = two ? o.accum2[k] : 0.f;
+                dense_opt_one(R, w, a, b, o.grad[k]);
                 o.accum[k] = a; o.theta[k] = w;
+                if (two) o.accum2[k] = b;
                 if (o.zero_grad) o.grad[k] = 0.f;
             }
         }

@@ -37,7 +37,7 @@ class _PrepArgs(ctypes.Structure):
                 ("cache_lin", c_void_p), ("cache_col", c_void_p), ("cache_off", c_void_p), ("nc", c_int),
                 ("wd", c_void_p), ("bias", c_void_p), ("S", c_void_p), ("base", c_void_p), ("B", c_int),
                 ("K0p", c_int), ("Dp", c_int), ("nf", c_int), ("ns", c_int), ("lin0", c_int), ("use_fm", c_int),
-                ("loss", c_void_p)]
+                ("loss", c_void_p), ("opt_step", c_void_p)]
 
 
 class _HeadArgs(ctypes.Structure):
@@ -55,7 +55,10 @@ class _OptMat(ctypes.Structure):
 
 class _DenseOptArgs(ctypes.Structure):
     _fields_ = [("theta", c_void_p), ("accum", c_void_p), ("grad", c_void_p), ("n", c_longlong), ("flat_lo", c_longlong),
-                ("lr", c_float), ("eps", c_float), ("nmat", c_int), ("zero_grad", c_int), ("mat", _OptMat * 4)]
+                ("lr", c_float), ("eps", c_float), ("nmat", c_int), ("zero_grad", c_int), ("mat", _OptMat * 4),
+                ("kind", c_int), ("_pad", c_int), ("accum2", c_void_p), ("step", c_void_p), ("b1", c_float), ("b2", c_float),
+                ("l1", c_float), ("l2", c_float), ("l2s", c_float), ("lrp", c_float), ("beta", c_float),
+                ("c1", c_float), ("c2", c_float)]
 
 
 def _r(x, m):
@@ -106,7 +109,7 @@ class FusedCTR:
 
     def __init__(self, vocab_sizes, num_dense=13, embedding_dim=64, model="deepfm", batch=4096, hidden=None,
                  sparse_optimizer=None, cache_threshold=0, lr=0.001, initial_accumulator_value=0.1, eps=1e-7,
-                 num_shards=None, dw_splits=8, seed=0, pack_linear=None):
+                 num_shards=None, dw_splits=8, seed=0, pack_linear=None, dense_optimizer=None):
         from .ctr import FusedEmbeddings
         ctx = get_context()
         if ctx.device.type != "cuda":
@@ -175,7 +178,18 @@ class FusedCTR:
         off = _r(off + max(vc, 1), 4)
         self.segs, self.n_theta = segs, off
         self.theta = torch.zeros(off, dtype=f32, device=dev)
-        self.accum = torch.full((off,), float(initial_accumulator_value), dtype=f32, device=dev)
+        # dense optimizer (tf.keras semantics): {"category": "adagrad" | "adam" | "ftrl", ...}; default Adagrad(lr)
+        from ..config import normalize_optimizer
+        dopt = normalize_optimizer(dense_optimizer or {"category": "adagrad", "learning_rate": lr,
+                                                        "initial_accumulator_value": initial_accumulator_value, "epsilon": eps})
+        if dopt["category"] not in ("adagrad", "adam", "ftrl"):
+            raise ValueError("fused dense optimizer: adagrad, adam or ftrl")
+        self.dense_opt = dopt
+        self.lr = lr = float(dopt["learning_rate"])
+        acc0 = float(dopt.get("initial_accumulator_value", 0.0)) if dopt["category"] in ("adagrad", "ftrl") else 0.0
+        self.accum = torch.full((off,), acc0, dtype=f32, device=dev)
+        self.accum2 = torch.zeros(off if dopt["category"] != "adagrad" else 4, dtype=f32, device=dev)
+        self.opt_step = torch.zeros(1, dtype=torch.int32, device=dev)
         self._ar = None
         if ctx.world > 1:     # gradients are produced straight into the peer-mapped all-reduce buffer
             from ..ops.p2p_allreduce import P2PAllReduce
@@ -233,8 +247,15 @@ class FusedCTR:
         assert L <= 4, "the fused optimizer kernel takes at most 4 weight matrices"
         oa = _DenseOptArgs()
         oa.theta, oa.accum, oa.grad = self.theta.data_ptr(), self.accum.data_ptr(), self.gtheta.data_ptr()
-        oa.n, oa.flat_lo, oa.lr, oa.eps = self.n_theta, segs["wout"][0], self.lr, self.eps
+        oa.n, oa.flat_lo, oa.lr, oa.eps = self.n_theta, segs["wout"][0], self.lr, float(self.dense_opt.get("epsilon", self.eps))
         oa.nmat, oa.zero_grad = L, 1
+        d = self.dense_opt
+        oa.kind = {"adagrad": 0, "adam": 1, "ftrl": 2}[d["category"]]
+        oa.accum2, oa.step = self.accum2.data_ptr(), self.opt_step.data_ptr()
+        oa.b1, oa.b2 = float(d.get("beta_1", 0.9)), float(d.get("beta_2", 0.999))
+        oa.l1, oa.l2 = float(d.get("l1_regularization_strength", 0.0)), float(d.get("l2_regularization_strength", 0.0))
+        oa.l2s, oa.lrp = float(d.get("l2_shrinkage_regularization_strength", 0.0)), float(d.get("learning_rate_power", -0.5))
+        oa.beta = float(d.get("beta", 0.0))
         for l in range(L):
             oa.mat[l].off, oa.mat[l].R, oa.mat[l].C = segs["W%d" % l][0], self.Hp[l], dims[l]
             oa.mat[l].Wb, oa.mat[l].WTb = self.Wb[l].data_ptr(), self.WTb[l].data_ptr()
@@ -326,7 +347,8 @@ class FusedCTR:
                        dense.data_ptr(), self.nd, self.view("cache_emb").data_ptr(), self.view("cache_lin").data_ptr(),
                        self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc, self.view("wd").data_ptr(),
                        self.view("bias").data_ptr(), self.S.data_ptr(), self.base.data_ptr(), B, self.K0p, self.Dp,
-                       self.nf, self.ns, self.lin0, int(self.use_fm), self.loss.data_ptr())
+                       self.nf, self.ns, self.lin0, int(self.use_fm), self.loss.data_ptr(),
+                       self.opt_step.data_ptr() if update else 0)
         _ck(lib.exb_prep(ctypes.byref(pa), B, self.Dp, st), "prep")
         self._mark("prep")
         dims = [self.K0p] + self.Hp

@@ -45,13 +45,62 @@ class FlatAdagrad:
         self.flat.addcdiv_(g, self.accum.sqrt().add_(self.eps), value=-self.lr)
 
 
+class FlatAdam(FlatAdagrad):
+    """tf.keras Adam over the flat buffer (the reference benchmark's --optimizer Adam)"""
+
+    def __init__(self, params, lr=0.001, beta_1=0.9, beta_2=0.999, eps=1e-7):
+        super().__init__(params, lr=lr, initial_accumulator_value=0.0, eps=eps)
+        self.b1, self.b2 = beta_1, beta_2
+        self.v = torch.zeros_like(self.accum)
+        self.t = torch.zeros((), dtype=torch.float32, device=self.flat.device)
+
+    def step(self):
+        g = self.grad
+        self.t += 1
+        self.accum.mul_(self.b1).add_(g, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+        lr_t = self.lr * torch.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        self.flat.sub_(lr_t * self.accum / (self.v.sqrt() + self.eps))
+
+
+class FlatFtrl(FlatAdagrad):
+    """tf.keras Ftrl over the flat buffer (defaults of the reference benchmark)"""
+
+    def __init__(self, params, lr=0.001, initial_accumulator_value=0.1, l1=0.0, l2=0.0, lr_power=-0.5):
+        super().__init__(params, lr=lr, initial_accumulator_value=initial_accumulator_value)
+        self.l1, self.l2, self.p = l1, l2, -lr_power
+        self.lin = torch.zeros_like(self.accum)
+
+    def step(self):
+        g, w = self.grad, self.flat
+        an = self.accum + g * g
+        sigma = (an.pow(self.p) - self.accum.pow(self.p)) / self.lr
+        self.lin.add_(g - sigma * w)
+        self.accum.copy_(an)
+        quad = an.pow(self.p) / self.lr + 2 * self.l2
+        self.flat.copy_((self.lin.clamp(-self.l1, self.l1) - self.lin) / quad)
+
+
+def make_flat_optimizer(params, config=None, lr=0.001):
+    """dense optimizer of the eager trainer from a Keras-style config ({"category": adagrad | adam | ftrl, ...})"""
+    from ..config import normalize_optimizer
+    c = normalize_optimizer(config or {"category": "adagrad", "learning_rate": lr})
+    if c["category"] == "adam":
+        return FlatAdam(params, lr=c["learning_rate"], beta_1=c["beta_1"], beta_2=c["beta_2"], eps=c["epsilon"])
+    if c["category"] == "ftrl":
+        return FlatFtrl(params, lr=c["learning_rate"], initial_accumulator_value=c["initial_accumulator_value"],
+                        l1=c["l1_regularization_strength"], l2=c["l2_regularization_strength"], lr_power=c["learning_rate_power"])
+    return FlatAdagrad(params, lr=c["learning_rate"], initial_accumulator_value=c.get("initial_accumulator_value", 0.1),
+                       eps=c.get("epsilon", 1e-7))
+
+
 class Trainer:
-    def __init__(self, model, lr=0.001, use_graph=True, allreduce="auto"):
+    def __init__(self, model, lr=0.001, use_graph=True, allreduce="auto", dense_optimizer=None):
         self.ctx = get_context()
         self.model = model
         self.device = self.ctx.device
         self.world = self.ctx.world
-        self.opt = FlatAdagrad(model.dense_parameters(), lr=lr)
+        self.opt = make_flat_optimizer(model.dense_parameters(), dense_optimizer, lr=lr)
         self.use_graph = use_graph and self.device.type == "cuda"
         self.graph = None
         self._static = None

@@ -96,3 +96,33 @@ def test_prefetch_next_batch_matches_plain(cuda_context, graph):
         curves.append(losses)
     for a, b in zip(*curves):
         assert abs(a - b) < 2e-4, curves
+
+
+@pytest.mark.parametrize("cfg", [{"category": "adam", "learning_rate": 0.01},
+                                 {"category": "ftrl", "learning_rate": 0.05, "l1_regularization_strength": 0.001},
+                                 {"category": "adagrad", "learning_rate": 0.05}])
+def test_fused_dense_optimizers_match_keras(cuda_context, cfg):
+    """the dense optimizer of the fused step (exb_dense_opt_kernel: adagrad / adam / ftrl) vs the Keras formulas"""
+    from test_optimizers import keras_reference
+    from openembedding_b200.context import get_context
+    from openembedding_b200.models.fused_dense import FusedCTR
+    ctx = get_context()
+    vocab = [1000, 50, 20000, 7, 3000] + [300] * 21
+    B = 256
+    m = FusedCTR(vocab, embedding_dim=8, model="deepfm", batch=B, cache_threshold=64,
+                 sparse_optimizer={"category": "adagrad", "learning_rate": 0.05}, dense_optimizer=dict(cfg))
+    theta0 = m.theta.detach().cpu().double().clone()
+    grads = []
+    for s in range(4):
+        b = _batch(vocab, B, ctx.device, seed=s)
+        m.forward_backward(*b, update=False)
+        torch.cuda.synchronize()
+        grads.append(m.gtheta.detach().cpu().double().clone())
+        m.forward_backward(*b, update=True)
+        torch.cuda.synchronize()
+    ctx.backend.engine.check()
+    ref = keras_reference(cfg, theta0.view(1, -1), [g.view(1, -1) for g in grads]).view(-1)
+    got = m.theta.detach().cpu().double()
+    err = float((got - ref).abs().max())
+    moved = float((ref - theta0).abs().max())
+    assert moved > 1e-4 and err < 2e-2 * moved + 1e-6, (cfg, err, moved)

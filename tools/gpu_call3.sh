@@ -11,7 +11,7 @@ run() { # name, extra env/args...
   grep '^{' gpurun_out/r2_bench_${name}_n$N.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d.get('push_update_phases_us'), d.get('sparse_counters'))"
 }
 EXTRA="" run v2 EXB_SPARSE_V2=1
-EXTRA="--prefetch" run v2pf EXB_SPARSE_V2=1
+EXTRA="--no-prefetch" run v2nopf EXB_SPARSE_V2=1
 EXTRA="" run v1 EXB_SPARSE_V2=0
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --impl baseline --steps 100 --warmup 10 > gpurun_out/r2_bench_base_n$N.log 2>&1; echo "base rc=$?"
 grep '^{' gpurun_out/r2_bench_base_n$N.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"
