@@ -130,6 +130,7 @@ def cuda():
         P(lib, "exb_plan_reset", c_int, [c_void_p, c_int, c_uint64])
         P(lib, "exb_pull2", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_int, c_uint64])
         P(lib, "exb_push2", c_int, [c_void_p, c_uint64, c_int, c_int, c_uint64])
+        P(lib, "exb_plan_set_dense_reduce", c_int, [c_void_p, ctypes.POINTER(c_uint64), c_uint64])
         P(lib, "exb_pull_plan", c_int, [c_void_p, c_uint64, c_uint64, c_int, c_int, c_uint64])
         P(lib, "exb_plan_memory", c_int, [c_void_p, u64p])
         P(lib, "exb_engine_status_ptr", c_uint64, [c_void_p])

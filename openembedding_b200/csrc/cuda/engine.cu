@@ -825,6 +825,18 @@ int exb_pull(void* ph, uint64_t ids, uint64_t out, int n_rows, uint64_t stream) 
                   (const TableDev*)e->d_tables, p->d, (const long long*)ids, (float*)out, n_rows));
     return 0;
 }
+// Attach (n > 0) or detach (n == 0) a dense-gradient all-reduce to this plan's push kernels: bufs[r] is rank r's
+// flat fp32 gradient buffer as mapped into this process (P2PAllReduce), n its length in floats (multiple of 4).
+// Every rank must attach the same n before its next push; the push then leaves the summed gradients in every buffer.
+int exb_plan_set_dense_reduce(void* ph, const uint64_t* bufs, uint64_t n) {
+    Plan* p = (Plan*)ph;
+    if (n % 4) return fail_msg("dense reduce: length must be a multiple of 4 floats");
+    for (int r = 0; r < EXB_MAX_PEERS; ++r) p->d.ar_buf[r] = (n && r < p->d.W) ? (float*)bufs[r] : nullptr;
+    for (int r = 0; r < p->d.W && n; ++r)
+        if (!p->d.ar_buf[r]) return fail_msg("dense reduce: peer buffer not mapped");
+    p->d.ar_n = p->d.W > 1 ? n : 0;
+    return 0;
+}
 int exb_push_update(void* ph, uint64_t ids, uint64_t grads, int n_rows, uint64_t stream) {
     Plan* p = (Plan*)ph;
     Engine* e = p->e;

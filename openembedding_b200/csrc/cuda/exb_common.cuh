@@ -91,6 +91,9 @@ struct PlanDev {
     SlotDev slot[2];                                // v2 batch slots
     unsigned* parity;                               // which slot is "current" (flipped by exb_push2_kernel)
     unsigned* inbox_vals[EXB_MAX_PEERS];            // peer mapped: count of every inbox entry (parallel to inbox_keys)
+    // dense-gradient all-reduce riding on the push kernel's cross-GPU barriers (exb_plan_set_dense_reduce; 0: off)
+    float* ar_buf[EXB_MAX_PEERS];                   // peer mapped flat gradient buffer of every rank
+    unsigned long long ar_n;                        // floats (multiple of 4)
 };
 #define EXB_TRACE_SLOTS 32
 

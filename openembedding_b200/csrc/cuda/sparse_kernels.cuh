@@ -405,6 +405,94 @@ __device__ __noinline__ void move_rows_dispatch(const TableDev& T, const float* 
     }
 }
 
+// gradient rows of a split-row feature (see pull_rows_split) are gathered from two places of the gradient row
+// and added into the accumulator row (mode 1) or stored into an inbox row (mode 2): columns [0, split) from src,
+// [split, dim) from src2, pad columns 0
+template <int LPR>
+__device__ __forceinline__ void accum_rows_split_t(const TableDev& T, const float* src, const float* src2, int split,
+                                                   float* dst, int mode, int lane) {
+    const int wstride = T.wstride, dim = T.dim;
+    constexpr int RP = 32 / LPR;
+    constexpr int U = LPR >= 8 ? 8 : LPR;              // rows in flight per lane group
+    const int gl = lane % LPR, sub = lane / LPR;
+    for (int cb = 0; cb < wstride; cb += LPR * 4) {    // one iteration unless the row is wider than 128 floats
+        const int c = cb + gl * 4;
+        const bool cin = c < wstride;
+#pragma unroll 1
+        for (int p0 = 0; p0 < LPR; p0 += U) {
+            float4 v[U];
+            float* d[U];
+            int m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = (p0 + u) * RP + sub;
+                const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
+                const float* s2 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src2, r);
+                d[u] = (float*)__shfl_sync(0xffffffffu, (unsigned long long)dst, r);
+                m[u] = __shfl_sync(0xffffffffu, mode, r);
+                if (!cin) m[u] = 0;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m[u]) {
+                    if (c + 4 <= split) v[u] = ld_stream_v4(s + c);
+                    else {
+                        float t[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = c + e;
+                            t[e] = col < split ? s[col] : (col < dim ? s2[col - split] : 0.f);
+                        }
+                        v[u] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (m[u] == 1) red_add_v4(d[u] + c, v[u]);                                   // accumulate
+                else if (m[u] == 2) *reinterpret_cast<float4*>(d[u] + c) = v[u];              // store (peer inbox)
+            }
+        }
+    }
+}
+__device__ __noinline__ void accum_rows_split(const TableDev& T, const float* src, const float* src2, int split,
+                                              float* dst, int mode, int lane) {
+    switch (T.lpr) {
+        case 1: accum_rows_split_t<1>(T, src, src2, split, dst, mode, lane); break;
+        case 2: accum_rows_split_t<2>(T, src, src2, split, dst, mode, lane); break;
+        case 4: accum_rows_split_t<4>(T, src, src2, split, dst, mode, lane); break;
+        case 8: accum_rows_split_t<8>(T, src, src2, split, dst, mode, lane); break;
+        case 16: accum_rows_split_t<16>(T, src, src2, split, dst, mode, lane); break;
+        default: accum_rows_split_t<32>(T, src, src2, split, dst, mode, lane); break;
+    }
+}
+
+// Dense-gradient all-reduce riding on the push kernel (P.ar_n > 0). Called by every thread of the grid between the
+// cross-GPU "counts published" barrier (every peer has entered its push kernel, so its dense gradients are final) and
+// the "update done" barrier: this rank sums its 1/W chunk of the flat gradient over every rank's buffer (peer loads)
+// and stores the sum into every rank's buffer (peer stores) -- the two-shot all-reduce of exb_ar_fused_kernel
+// (dense_kernels.cu) without a launch or cross-GPU barriers of its own. Chunk r of a peer's buffer is read and then
+// written by rank r only, so the in-place update needs no extra ordering; the sums are bit-identical on every rank.
+// The caller's last barrier must WAIT for the peers (peer_barrier(P, true)): the dense optimizer runs next.
+__device__ __forceinline__ void dense_reduce_rider(const PlanDev& P) {
+    const int W = P.W;
+    const long long n = (long long)P.ar_n;
+    const long long per = ((n + W - 1) / W + 3) & ~3ll;
+    const long long lo = per * P.rank, hi = min(n, lo + per);
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
+        float4 v[EXB_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < EXB_MAX_PEERS; ++r)
+            if (r < W) v[r] = __ldcg(reinterpret_cast<const float4*>(P.ar_buf[r] + i));
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < EXB_MAX_PEERS; ++r)
+            if (r < W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < EXB_MAX_PEERS; ++r)
+            if (r < W) __stcg(reinterpret_cast<float4*>(P.ar_buf[r] + i), s);
+    }
+}
+
 // non-bulk optimizer path (rows that do not fit the warp buffer, dim < 4): out of line, see pull_rows_slow
 template <int LPR>
 __device__ __forceinline__ void apply_rows(const TableDev& T, const PlanDev& P, float* accbase,
@@ -694,7 +782,10 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
                 }
             }
         }
-        move_rows_dispatch(T, src, dst, mode, lane);
+        if (S.feat_split[f] < T.dim)      // split-row feature: the gradient row comes from two places of the gradient matrix
+            accum_rows_split(T, src, grads + (size_t)b * P.io_stride + S.feat_off2[f], S.feat_split[f], dst, mode, lane);
+        else
+            move_rows_dispatch(T, src, dst, mode, lane);
     }
 
     EXB_STAMP(1);
@@ -713,6 +804,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             peer_barrier(P);
         });
         EXB_STAMP(2);
+        if (P.ar_n) dense_reduce_rider(P);     // peer loads / stores in flight under the combine phase
         // ---------------- P3: combine inbox entries of every remote source
         const unsigned* mycnt = P.inbox_cnt[rank];
         block_task_prefix(mycnt, W * PT, s_prefix);
@@ -822,7 +914,9 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     grid_barrier(P, false, [&]() {   // P5 wrote local memory only; the sys release is in peer_barrier
         for (int i = threadIdx.x; i < PT; i += blockDim.x) P.ucount[i * EXB_CTR_STRIDE] = 0;
         if (threadIdx.x == 0) atomicAdd(&P.stats[1], (unsigned long long)n_rows * P.F);
-        if (W > 1) peer_barrier(P, false);   // signal only: the next pull waits (peer_wait)
+        // signal only: the next pull waits (peer_wait) -- unless the dense reduction rode along, whose result the
+        // next kernel of this stream (the dense optimizer) reads
+        if (W > 1) peer_barrier(P, P.ar_n != 0);
     });
     EXB_STAMP(6);
 #undef EXB_STAMP

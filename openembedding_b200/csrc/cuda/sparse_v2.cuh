@@ -287,63 +287,6 @@ __device__ __forceinline__ void zero_rows(const TableDev& T, float* dst, int on,
     }
 }
 
-// gradient rows of a split-row feature (see pull_rows_split) are gathered from two places of the gradient row
-// and added into the accumulator row: columns [0, split) from src, [split, dim) from src2, pad columns 0
-template <int LPR>
-__device__ __forceinline__ void accum_rows_split_t(const TableDev& T, const float* src, const float* src2, int split,
-                                                   float* dst, int mode, int lane) {
-    const int wstride = T.wstride, dim = T.dim;
-    constexpr int RP = 32 / LPR;
-    constexpr int U = LPR >= 8 ? 8 : LPR;              // rows in flight per lane group
-    const int gl = lane % LPR, sub = lane / LPR;
-    for (int cb = 0; cb < wstride; cb += LPR * 4) {    // one iteration unless the row is wider than 128 floats
-        const int c = cb + gl * 4;
-        const bool cin = c < wstride;
-#pragma unroll 1
-        for (int p0 = 0; p0 < LPR; p0 += U) {
-            float4 v[U];
-            float* d[U];
-            int m[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = (p0 + u) * RP + sub;
-                const float* s = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src, r);
-                const float* s2 = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)src2, r);
-                d[u] = (float*)__shfl_sync(0xffffffffu, (unsigned long long)dst, r);
-                m[u] = __shfl_sync(0xffffffffu, mode, r);
-                if (!cin) m[u] = 0;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m[u]) {
-                    if (c + 4 <= split) v[u] = ld_stream_v4(s + c);
-                    else {
-                        float t[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int col = c + e;
-                            t[e] = col < split ? s[col] : (col < dim ? s2[col - split] : 0.f);
-                        }
-                        v[u] = make_float4(t[0], t[1], t[2], t[3]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (m[u]) red_add_v4(d[u] + c, v[u]);
-        }
-    }
-}
-__device__ __noinline__ void accum_rows_split(const TableDev& T, const float* src, const float* src2, int split,
-                                              float* dst, int mode, int lane) {
-    switch (T.lpr) {
-        case 1: accum_rows_split_t<1>(T, src, src2, split, dst, mode, lane); break;
-        case 2: accum_rows_split_t<2>(T, src, src2, split, dst, mode, lane); break;
-        case 4: accum_rows_split_t<4>(T, src, src2, split, dst, mode, lane); break;
-        case 8: accum_rows_split_t<8>(T, src, src2, split, dst, mode, lane); break;
-        case 16: accum_rows_split_t<16>(T, src, src2, split, dst, mode, lane); break;
-        default: accum_rows_split_t<32>(T, src, src2, split, dst, mode, lane); break;
-    }
-}
-
 // where does row `id` of table T live on rank `o`? (array: direct address; hash: probe in the owner's key slab)
 // returns the mode for rows_to: 1 (src valid) or 2 (row not materialised yet -> initializer value)
 __device__ __forceinline__ int resolve_row(const TableDev& T, unsigned long long id, int o, const float** src) {
@@ -578,6 +521,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
             peer_barrier(P);
         });
         EXB_STAMP(3);
+        if (P.ar_n) dense_reduce_rider(P);     // dense-gradient all-reduce on this kernel's barriers (sparse_kernels.cuh)
         // ---------------- P3: fold the other ranks' pre-reduced entries into this rank's map
         const unsigned* mycnt = P.inbox_cnt[rank];
         block_task_prefix(mycnt, W * PT, s_prefix);
@@ -701,7 +645,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
             atomicAdd(&P.stats[1], (unsigned long long)n_rows * P.F);
             *P.parity = __ldcg(P.parity) ^ 1u;
         }
-        if (W > 1) peer_barrier(P, false);
+        if (W > 1) peer_barrier(P, P.ar_n != 0);
     });
     EXB_STAMP(7);
 #undef EXB_STAMP

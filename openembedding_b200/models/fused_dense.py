@@ -142,7 +142,7 @@ class FusedCTR:
         # optimizer rows of the two-variables-per-feature layout of the reference benchmark
         # (criteo_deepctr.py:60-110). Same math per element; the checkpoint then holds one variable per feature.
         if pack_linear is None:
-            pack_linear = os.environ.get("EXB_PACK_LINEAR", "1") != "0" and os.environ.get("EXB_SPARSE_V2", "1") != "0"
+            pack_linear = os.environ.get("EXB_PACK_LINEAR", "1") != "0"
         self.pack_linear = bool(pack_linear)
         if self.pack_linear:
             specs = [{"vocab": self.vocab[f], "dim": embedding_dim + 1, "col": f, "initializer": zero} for f in self.server]
@@ -191,10 +191,18 @@ class FusedCTR:
         self.accum2 = torch.zeros(off if dopt["category"] != "adagrad" else 4, dtype=f32, device=dev)
         self.opt_step = torch.zeros(1, dtype=torch.int32, device=dev)
         self._ar = None
+        self._rider = False
+        self.overlap = os.environ.get("EXB_OVERLAP", "0") == "1"
         if ctx.world > 1:     # gradients are produced straight into the peer-mapped all-reduce buffer
             from ..ops.p2p_allreduce import P2PAllReduce
             self._ar = P2PAllReduce(ctx, off)
             self.gtheta = self._ar.grad
+            # the reduction rides on the sparse push kernel's cross-GPU barriers instead of being a kernel with two
+            # barriers of its own (EXB_AR_RIDER=0: separate exb_ar_fused_kernel launch)
+            self._rider = (os.environ.get("EXB_AR_RIDER", "1") != "0" and not self.overlap
+                           and hasattr(self.group, "set_dense_reduce"))
+            if self._rider:
+                self.group.set_dense_reduce(self._ar.bufs, off)
         else:
             self.gtheta = torch.zeros(off, dtype=f32, device=dev)
         gen = torch.Generator(device="cpu").manual_seed(seed)
@@ -335,8 +343,9 @@ class FusedCTR:
         self._mark("start")
         g = self.group
         v2 = getattr(g, "v2", False) and update
-        if pulled and v2:
-            g._armed[0] = (g._key(ids), "pull")        # rows + plan of this batch came with the previous step's tail
+        if pulled:
+            if v2:
+                g._armed[0] = (g._key(ids), "pull")    # rows + plan of this batch came with the previous step's tail
         elif v2:
             g.pull(ids, out=self.X32, train=True)      # gather + plan of the batch in one launch
         else:
@@ -408,19 +417,19 @@ class FusedCTR:
             if not forked:
                 self.group.push_update(ids, self.G32)
                 self._mark("push_update")
-            tail = next_ids is not None and v2 and not forked
+            tail = next_ids is not None and not forked
             if tail:      # next batch: rows into X32 (free since the dX1 GEMM) + plan, beside the dense optimizer
                 cur = torch.cuda.current_stream(self.dev)
                 self._ev_fork.record(cur)
                 self._s2.wait_event(self._ev_fork)
                 with torch.cuda.stream(self._s2):
-                    g.pull(next_ids, out=self.X32, train=True)
+                    g.pull(next_ids, out=self.X32, train=v2)
                     self._ev_plan.record(self._s2)
             # Adagrad + bf16 weight refresh + gradient clearing: one kernel (world > 1: behind the all-reduce,
             # in the same kernel)
             # world > 1: the all-reduce runs on one CTA per SM (every CTA polls peer flags); the optimizer kernel
             # is chained behind it with a programmatic dependent launch instead of sharing its grid
-            if self._ar is not None:
+            if self._ar is not None and not self._rider:
                 self._ar()
                 self._mark("allreduce")
             _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
@@ -442,7 +451,7 @@ class FusedCTR:
         head = 1 if (self.mn_major and self.Hp[-1] <= 512) else 2
         gemms = (1 if self.chain_fwd else L) + (1 if self.use_chain else 2 * L)   # persistent chains: fwd, bwd
         n = 1 + prep + gemms + head + (1 if self.nc else 0) + 1 + 1      # pull prep GEMMs head cache push optimizer
-        return n + (1 if self._ar is not None else 0)
+        return n + (1 if self._ar is not None and not self._rider else 0)
 
     # ---- fp32 torch reference of the dense math on the current X32 (tests)
     def reference(self, ids, dense, labels):
@@ -513,12 +522,10 @@ class FusedTrainer:
     def step(self, ids, dense, labels, next_ids=None):
         g = self.m.group
         v2 = getattr(g, "v2", False)
-        if not v2:
-            next_ids = None
-        pulled = v2 and self._x32_key is not None and self._x32_key == g._key(ids)
+        pulled = self._x32_key is not None and self._x32_key == g._key(ids)
         tail = next_ids is not None
         if not self.use_graph:
-            if not pulled and self._x32_key is not None:
+            if v2 and not pulled and self._x32_key is not None:
                 g.reset_slot(0)                     # a prefetched batch that is not the one trained now
             loss = self.m.forward_backward(ids, dense, labels, next_ids=next_ids, pulled=pulled)
             self._x32_key = g._key(next_ids) if tail else None
@@ -533,7 +540,7 @@ class FusedTrainer:
             s["labels"].copy_(labels, non_blocking=True)
         if tail:
             s["next_ids"].copy_(next_ids, non_blocking=True)
-        if not pulled and self._x32_key is not None:
+        if v2 and not pulled and self._x32_key is not None:
             g.reset_slot(0)                         # drop the prefetched plan: this is a different batch
         key = (not pulled, tail)
         gr = self._graphs.get(key)

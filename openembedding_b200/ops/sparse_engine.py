@@ -352,8 +352,6 @@ class SparsePlan:
         self.feat_split = [int(x) for x in feat_split] if feat_split is not None else None
         self.feat_offsets2 = [int(x) for x in feat_offsets2] if feat_offsets2 is not None else None
         if self.feat_split is not None:
-            if os.environ.get("EXB_SPARSE_V2", "1") == "0":
-                raise RuntimeError("split-row features need the v2 sparse kernels (EXB_SPARSE_V2=1)")
             fo2 = (ctypes.c_int32 * self.F)(*self.feat_offsets2)
             fsp = (ctypes.c_int32 * self.F)(*self.feat_split)
             self.h = self.lib.exb_plan_create2(engine.h, self.F, ft, fo, fc, self.ncols, self.B, self.io_stride, fo2, fsp)
@@ -364,7 +362,10 @@ class SparsePlan:
         self.connected = engine.world == 1
         # v2 ("plan once per step", csrc/cuda/sparse_v2.cuh): ids are de-duplicated once per batch into one of two
         # batch slots; pull moves unique remote rows, push moves pre-reduced rows. EXB_SPARSE_V2=0: v1 kernels.
-        self.v2 = os.environ.get("EXB_SPARSE_V2", "1") != "0"
+        # default: v2 on one GPU (measured 0.236 vs 0.267 ms/step), v1 with more (N=2: 0.319 vs 0.354 ms/step -- the
+        # extra phases of the pre-reduced push cost more than the halved NVLink rows buy; profiles/r2/sparse_v2.md)
+        env = os.environ.get("EXB_SPARSE_V2")
+        self.v2 = (env != "0") if env is not None else (engine.world == 1)
         # EXB_PULL2=1: training pulls of world > 1 move UNIQUE remote rows (exb_pull2_kernel: gather unique rows,
         # grid barrier, expand). Measured slower than the one-pass gather on 2 and 8 B200s (the step is bound by the
         # number of dependent phases, not by NVLink bytes -- profiles/r2/sparse_v2.md), hence off by default.
@@ -441,6 +442,11 @@ class SparsePlan:
             # the plan was prefetched: plain gather
         _native.cuda_check(self.lib.exb_pull(self.h, ids.data_ptr(), out.data_ptr(), n, self._stream()), "pull")
         return out
+
+    def set_dense_reduce(self, bufs, n):
+        """attach (n > 0) / detach (n == 0) a dense-gradient all-reduce to this plan's push kernels: `bufs` are every
+        rank's peer-mapped flat fp32 gradient buffers (P2PAllReduce.bufs). Collective: every rank, same n."""
+        _native.cuda_check(self.lib.exb_plan_set_dense_reduce(self.h, bufs, int(n)), "set_dense_reduce")
 
     def push_update(self, ids, grads):
         assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous()

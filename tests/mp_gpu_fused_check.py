@@ -29,7 +29,8 @@ def main():
     ids = torch.stack([torch.randint(0, v, (B,), generator=g) for v in vocab], dim=1).contiguous().to(ctx.device)
     dense = torch.rand(B, 13, generator=g).to(ctx.device)
     labels = (torch.rand(B, generator=g) < 0.3).float().to(ctx.device)
-    losses = [float(tr.step(ids, dense, labels)) for _ in range(12)]
+    nxt = ids if os.environ.get("EXB_TEST_PREFETCH") == "1" else None      # pull the next batch in the step's tail
+    losses = [float(tr.step(ids, dense, labels, next_ids=nxt)) for _ in range(12)]
     torch.cuda.synchronize()
     ctx.backend.engine.check()
     assert losses[-1] < losses[0] - 0.01, losses
@@ -39,7 +40,8 @@ def main():
     assert torch.equal(theta, ref), "dense replicas diverged: %g" % float((theta - ref).abs().max())
     dist.barrier()
     if rank == 0:
-        print("MP_GPU_FUSED_PASSED loss %.4f -> %.4f" % (losses[0], losses[-1]))
+        print("MP_GPU_FUSED_PASSED loss %.4f -> %.4f theta_sum %.17g rider %d" %
+              (losses[0], losses[-1], float(theta.double().abs().sum()), int(m._rider)))
     dist.destroy_process_group()
 
 

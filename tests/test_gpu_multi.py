@@ -51,4 +51,18 @@ def test_mp_engine_allreduce_checkpoint(n):
 def test_mp_fused_step_two_ranks():
     """the product step (FusedCTR + CUDA graph) trains on 2 ranks and the ranks stay bit-identical replicas"""
     rc, out = _torchrun(2, "tests/mp_gpu_fused_check.py")
+    assert rc == 0 and "MP_GPU_FUSED_PASSED" in out and "rider 1" in out, out[-4000:]
+    # the dense all-reduce riding on the push kernel gives the parameters of the stand-alone kernel (not bit for bit:
+    # the sparse gradient accumulation uses float atomics, whose order varies from run to run)
+    rc2, out2 = _torchrun(2, "tests/mp_gpu_fused_check.py", env={"EXB_AR_RIDER": "0"})
+    assert rc2 == 0 and "MP_GPU_FUSED_PASSED" in out2 and "rider 0" in out2, out2[-4000:]
+    tsum = lambda o: float(o.split("theta_sum ")[1].split()[0])
+    assert abs(tsum(out) - tsum(out2)) < 1e-6 * abs(tsum(out2)), (tsum(out), tsum(out2))
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs on the box")
+@pytest.mark.parametrize("v2", ["0", "1"])
+def test_mp_fused_step_prefetch(v2):
+    """same step prefetching the next batch in its tail, with the v1 / planned (v2) sparse kernels at world 2"""
+    rc, out = _torchrun(2, "tests/mp_gpu_fused_check.py", env={"EXB_SPARSE_V2": v2, "EXB_TEST_PREFETCH": "1"})
     assert rc == 0 and "MP_GPU_FUSED_PASSED" in out, out[-4000:]

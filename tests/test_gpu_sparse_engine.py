@@ -151,15 +151,17 @@ def test_virtual_ranks(world):
 
 @pytest.mark.parametrize("world,mode", [(1, "train"), (1, "prefetch"), (2, "train"), (3, "prefetch"), (4, "train"),
                                         (8, "prefetch")])
-def test_planned_batches(world, mode):
+def test_planned_batches(world, mode, monkeypatch):
     """v2 path end to end: de-duplicated plan, unique-row pull (exb_pull2_kernel), pre-reduced push, prefetch"""
+    monkeypatch.setenv("EXB_SPARSE_V2", "1")        # the default is v2 only on one GPU
     specs = [(64, 100000, False), (1, 100000, False), (9, 3, False), (16, 0, True), (4, 77, False), (200, 50, False)]
     err = _run(world, specs, batch=192, steps=4, opt_cfg=ADAGRAD, init_cfg=UNIFORM, mode=mode)
     assert err < 5e-4, err
 
 
-def test_planned_test_optimizer_counts():
+def test_planned_test_optimizer_counts(monkeypatch):
     """the `test` optimizer consumes the per-id counts: they must survive de-duplication and pre-reduction"""
+    monkeypatch.setenv("EXB_SPARSE_V2", "1")
     cfg = {"category": "test", "learning_rate": 0.05}
     err = _run(2, [(16, 300, False), (8, 0, True)], batch=128, steps=4, opt_cfg=cfg, init_cfg=UNIFORM, mode="train")
     assert err < 5e-3, err
@@ -257,9 +259,10 @@ def test_checkpoint_row_access_and_rehash():
     e.close()
 
 
-@pytest.mark.parametrize("world,dim", [(1, 10), (1, 65), (2, 65), (2, 17)])
-def test_split_row_feature(world, dim):
+@pytest.mark.parametrize("world,dim,v2", [(1, 10, 1), (1, 65, 1), (2, 65, 1), (2, 17, 1), (1, 65, 0), (2, 65, 0), (2, 10, 0)])
+def test_split_row_feature(world, dim, v2, monkeypatch):
     """one table row [embedding(D) | linear(1)] feeding two places of the activation / gradient row"""
+    monkeypatch.setenv("EXB_SPARSE_V2", str(v2))
     from openembedding_b200.ops.sparse_engine import CudaEngine
     torch.manual_seed(3)
     dev = torch.device("cuda", 0)
