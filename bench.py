@@ -329,6 +329,11 @@ def main():
                        "global_batch": gb, "seq_len": 1, "parallelism": "dp%d + row-sharded embeddings (id %% %d) over NVLink" % (world, world),
                        "vocab_rows_total": rows, "tables_fp32_gb": round(rows * (a.dim + 1) * 4 * 2 / 2 ** 30, 1),
                        "cache_threshold": a.cache, "cuda_graph": not a.no_graph, "engine": engine, "prefetch": prefetch,
+                       "sparse_kernels": ("v2 (planned batch, pre-reduced push)" if getattr(getattr(model, "group", None), "v2", False)
+                                          else "v1 (stateless pull, dispatch/combine push)") if engine == "fused" else "v1 (eager layers)",
+                       "dense_allreduce": ("none (1 GPU)" if world == 1 else
+                                           "inside the sparse push kernel" if getattr(model, "_rider", False) else
+                                           "stand-alone P2P kernel"),
                        "l2_policy": "inputs larger than L2: %d distinct random batches over a %.0f GB table working set" % (
                            a.pool, rows * (a.dim + 1) * 8 / 2 ** 30)},
             "clocks": clocks,

@@ -465,18 +465,27 @@ __device__ __noinline__ void accum_rows_split(const TableDev& T, const float* sr
     }
 }
 
-// Dense-gradient all-reduce riding on the push kernel (P.ar_n > 0). Called by every thread of the grid between the
-// cross-GPU "counts published" barrier (every peer has entered its push kernel, so its dense gradients are final) and
-// the "update done" barrier: this rank sums its 1/W chunk of the flat gradient over every rank's buffer (peer loads)
-// and stores the sum into every rank's buffer (peer stores) -- the two-shot all-reduce of exb_ar_fused_kernel
-// (dense_kernels.cu) without a launch or cross-GPU barriers of its own. Chunk r of a peer's buffer is read and then
-// written by rank r only, so the in-place update needs no extra ordering; the sums are bit-identical on every rank.
-// The caller's last barrier must WAIT for the peers (peer_barrier(P, true)): the dense optimizer runs next.
-__device__ __forceinline__ void dense_reduce_rider(const PlanDev& P) {
-    const int W = P.W;
+// Dense-gradient all-reduce riding on the push kernel (P.ar_n > 0): the two-shot all-reduce of exb_ar_fused_kernel
+// (dense_kernels.cu) without a launch or cross-GPU barriers of its own. Two calls by every thread of the grid:
+//   dense_reduce_gather   after the cross-GPU "counts published" barrier (every peer has entered its push kernel, so
+//                         its dense gradients are final): this rank sums its 1/W chunk of the flat gradient over every
+//                         rank's buffer (peer loads, their latency hides under the combine phase) into its own buffer;
+//   dense_reduce_scatter  after the next grid barrier: the summed chunk goes to every peer's buffer (peer stores, in
+//                         flight under the apply phase; the kernel's last barrier releases them at system scope).
+// Chunk r of a peer's buffer is read and then written by rank r only, so the in-place update needs no extra ordering;
+// the sums are bit-identical on every rank. The caller's last barrier must WAIT for the peers (peer_barrier(P, true)):
+// the dense optimizer runs next. (One call doing both cost 8-10 us of grid-barrier time at 8 GPUs: the barrier's
+// fence waits for the NVLink stores in flight.)
+__device__ __forceinline__ void dense_reduce_span(const PlanDev& P, long long& lo, long long& hi) {
     const long long n = (long long)P.ar_n;
-    const long long per = ((n + W - 1) / W + 3) & ~3ll;
-    const long long lo = per * P.rank, hi = min(n, lo + per);
+    const long long per = ((n + P.W - 1) / P.W + 3) & ~3ll;
+    lo = per * P.rank;
+    hi = min(n, lo + per);
+}
+__device__ __forceinline__ void dense_reduce_gather(const PlanDev& P) {
+    const int W = P.W;
+    long long lo, hi;
+    dense_reduce_span(P, lo, hi);
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
         float4 v[EXB_MAX_PEERS];
@@ -487,9 +496,19 @@ __device__ __forceinline__ void dense_reduce_rider(const PlanDev& P) {
 #pragma unroll
         for (int r = 0; r < EXB_MAX_PEERS; ++r)
             if (r < W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        __stcg(reinterpret_cast<float4*>(P.ar_buf[P.rank] + i), s);
+    }
+}
+__device__ __forceinline__ void dense_reduce_scatter(const PlanDev& P) {
+    const int W = P.W, rank = P.rank;
+    long long lo, hi;
+    dense_reduce_span(P, lo, hi);
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
+        const float4 s = __ldcg(reinterpret_cast<const float4*>(P.ar_buf[rank] + i));
 #pragma unroll
         for (int r = 0; r < EXB_MAX_PEERS; ++r)
-            if (r < W) __stcg(reinterpret_cast<float4*>(P.ar_buf[r] + i), s);
+            if (r < W && r != rank) __stcg(reinterpret_cast<float4*>(P.ar_buf[r] + i), s);
     }
 }
 
@@ -804,7 +823,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
             peer_barrier(P);
         });
         EXB_STAMP(2);
-        if (P.ar_n) dense_reduce_rider(P);     // peer loads / stores in flight under the combine phase
+        if (P.ar_n) dense_reduce_gather(P);    // peer loads in flight under the combine phase
         // ---------------- P3: combine inbox entries of every remote source
         const unsigned* mycnt = P.inbox_cnt[rank];
         block_task_prefix(mycnt, W * PT, s_prefix);
@@ -840,6 +859,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     EXB_STAMP(3);
     grid_barrier(P, false, [&]() {});
     EXB_STAMP(4);
+    if (P.ar_n) dense_reduce_scatter(P);       // peer stores drain under the apply phase
 
     // ---------------- P5: apply optimizer to every unique row
     int* s_chunk = s_prefix + 256;     // the combine phase is over: its 1025-entry prefix array is free again

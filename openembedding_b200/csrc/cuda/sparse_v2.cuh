@@ -521,7 +521,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
             peer_barrier(P);
         });
         EXB_STAMP(3);
-        if (P.ar_n) dense_reduce_rider(P);     // dense-gradient all-reduce on this kernel's barriers (sparse_kernels.cuh)
+        if (P.ar_n) dense_reduce_gather(P);    // dense-gradient all-reduce on this kernel's barriers (sparse_kernels.cuh)
         // ---------------- P3: fold the other ranks' pre-reduced entries into this rank's map
         const unsigned* mycnt = P.inbox_cnt[rank];
         block_task_prefix(mycnt, W * PT, s_prefix);
@@ -555,6 +555,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
     EXB_STAMP(4);
     grid_barrier(P, false, [&]() {});
     EXB_STAMP(5);
+    if (P.ar_n) dense_reduce_scatter(P);       // peer stores drain under the apply phase
 
     // ---------------- P5: optimizer on every unique row this rank owns; every map entry is reset
     int* s_chunk = s_prefix + 256;

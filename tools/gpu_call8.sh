@@ -1,16 +1,13 @@
 #!/bin/bash
-# N-GPU call: multi-GPU tests + bench variants around the dense-reduce rider at N = $1
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_pytest8_n$N.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/r2_pytest8_n$N.log
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -k fused > gpurun_out/r2_pytest8_n$N.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r2_pytest8_n$N.log
 run() { # name, extra env/args...
   name=$1; shift
   timeout 600 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 300 --warmup 20 $EXTRA > gpurun_out/r2_bench8_${name}_n$N.log 2>&1
   echo "$name rc=$?"
   grep '^{' gpurun_out/r2_bench8_${name}_n$N.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d.get('push_update_phases_us'))"
 }
-EXTRA="" run rider_pf X=1
-EXTRA="--no-prefetch" run rider_nopf X=1
-EXTRA="" run rider_pf_unpacked EXB_PACK_LINEAR=0
-EXTRA="" run norider_pf EXB_AR_RIDER=0
+EXTRA="" run default X=1
+EXTRA="" run default_again X=1
