@@ -200,7 +200,8 @@ class Variable:
             rows = ctx.backend.pull(self.variable, flat)
         if timers.enabled:
             timers.add_count("pull_indices", flat.numel())
-            timers.add_count("pull_unique", int(torch.unique(flat).numel()))
+            if not flat.is_cuda:      # on the GPU the engine counts unique rows itself (engine.status(): pull_unique /
+                timers.add_count("pull_unique", int(torch.unique(flat).numel()))   # update_unique): no sync here
         return rows.reshape(tuple(indices.shape) + tuple(self._shape[1:])).to(self._tdtype)
 
     def _push(self, indices, grads):

@@ -1,15 +1,16 @@
 """Fused DeepFM / Wide&Deep training step on hand-written sm_100a kernels only.
 
-Per step and per GPU (15 launches, captured in one CUDA graph by ``FusedTrainer``):
+Per step and per GPU (10 launches at world 1, captured in one CUDA graph by ``FusedTrainer``):
 
-    pull (peer loads, UBLKCP)            sparse_kernels.cuh
-    prep                                 dense_kernels.cu   X32 -> A0, A0^T (bf16), FM sums, base logit
+    pull + plan (peer loads, cp.async)   sparse_v2.cuh / sparse_kernels.cuh   (prefetched in the previous step's tail)
+    prep                                 dense_kernels.cu   X32 -> A0 (bf16), FM sums, base logit
     3x GEMM fwd  (tcgen05, relu, ones)   gemm_tcgen05.cu
     head         (loss, dlogit, dZ_L)    dense_kernels.cu
-    3x GEMM dX   (tcgen05, relu mask / FM-fused fp32 embedding gradient)
-    3x GEMM dW   (tcgen05, split-K, fp32 red.add)
-    cachegrad, push_update (P2P dispatch + combine + sparse optimizer), P2P all-reduce,
-    Adagrad(flat) + bf16 weight refresh
+    backward chain: 3x dX (relu mask / FM-fused fp32 embedding gradient) + 3x dW (MN-major operands, split-K,
+                 TMA reduce-add) as ONE persistent kernel (exb_gemm_chain_kernel)
+    cachegrad, push_update (P2P dispatch + combine + sparse optimizer; world > 1: the dense-gradient all-reduce
+                 rides on its cross-GPU barriers),
+    Adagrad / Adam / FTRL (flat) + bf16 weight refresh  ||  pull + plan of the NEXT batch on a side stream
 
 No cuBLAS, no NCCL, no torch op on the step. Biases are folded into the GEMMs through a
 constant "ones" column, so a layer is exactly one GEMM in each direction.

@@ -4,7 +4,9 @@ The reference delegates this to Horovod/NCCL (`hvd.DistributedOptimizer(op=hvd.S
 examples/criteo_deepctr_network.py:54). Here:
 
 * ``mode="p2p"``  -- the product path: one-shot / two-shot reduction kernel over
-  peer-mapped buffers (``csrc/cuda/allreduce.cu``), no NCCL on the step;
+  peer-mapped buffers (``exb_ar_fused_kernel`` in ``csrc/cuda/dense_kernels.cu``), no NCCL on the step; the fused
+  trainer goes one step further and sums the gradients inside the sparse push kernel (``dense_reduce_gather`` /
+  ``dense_reduce_scatter`` in ``csrc/cuda/sparse_kernels.cuh``);
 * ``mode="nccl"`` -- the baseline / cross-check path (``torch.distributed.all_reduce``).
 """
 import os
