@@ -509,18 +509,26 @@ class FusedTrainer:
 
     supports_prefetch = True
     want_prefetch = True         # ``make_pipeline`` runs one batch ahead: the next batch's pull overlaps this step's tail
+    supports_stable_inputs = True
+    MAX_STABLE_GRAPHS = 64
 
     def __init__(self, model, use_graph=True):
         self.m, self.ctx = model, model.ctx
         self.device, self.world = model.dev, model.ctx.world
         self.use_graph = use_graph
-        self._graphs, self._static = {}, None      # (pull up front?, prefetch pull at the tail?) -> CUDAGraph
+        self._graphs, self._static = {}, None      # (pull up front?, prefetch pull at the tail?[, input addresses]) -> CUDAGraph
+        self._stable = {}                          # stable-input graph key -> the caller's tensors (kept alive)
         self.graph = None
         self._ar = model._ar
         self._x32_key = None         # key of the batch whose rows + plan the last step prefetched into X32
         self._warm = False
 
-    def step(self, ids, dense, labels, next_ids=None):
+    def step(self, ids, dense, labels, next_ids=None, stable=False):
+        """``stable=True``: the caller keeps the four input tensors alive at fixed addresses and refills them in place
+        (an input pipeline's device buffers, a resident pool of batches). In the steady state (this batch was
+        prefetched, the next one is announced) the graph is then captured directly on those tensors -- one graph per
+        distinct (ids, dense, labels, next_ids) address tuple, at most MAX_STABLE_GRAPHS -- instead of copying the
+        inputs into the trainer's own static buffers first (four device copies per step)."""
         g = self.m.group
         v2 = getattr(g, "v2", False)
         pulled = self._x32_key is not None and self._x32_key == g._key(ids)
@@ -535,18 +543,24 @@ class FusedTrainer:
         if self._static is None:
             self._static = {"ids": ids.clone(), "dense": dense.clone(), "labels": labels.clone(), "next_ids": ids.clone()}
         s = self._static
-        if ids.data_ptr() != s["ids"].data_ptr():
-            s["ids"].copy_(ids, non_blocking=True)
-            s["dense"].copy_(dense, non_blocking=True)
-            s["labels"].copy_(labels, non_blocking=True)
-        if tail:
-            s["next_ids"].copy_(next_ids, non_blocking=True)
+        key = (not pulled, tail)
+        if stable and pulled and tail and self._warm:
+            skey = key + (ids.data_ptr(), dense.data_ptr(), labels.data_ptr(), next_ids.data_ptr())
+            if skey in self._graphs or len(self._stable) < self.MAX_STABLE_GRAPHS:
+                key = skey
+                s = self._stable.setdefault(skey, {"ids": ids, "dense": dense, "labels": labels, "next_ids": next_ids})
+        if s is self._static:
+            if ids.data_ptr() != s["ids"].data_ptr():
+                s["ids"].copy_(ids, non_blocking=True)
+                s["dense"].copy_(dense, non_blocking=True)
+                s["labels"].copy_(labels, non_blocking=True)
+            if tail:
+                s["next_ids"].copy_(next_ids, non_blocking=True)
         if v2 and not pulled and self._x32_key is not None:
             g.reset_slot(0)                         # drop the prefetched plan: this is a different batch
-        key = (not pulled, tail)
         gr = self._graphs.get(key)
         if gr is None:
-            gr = self._capture(key)
+            gr = self._capture(key, s)
         gr.replay()
         # replays bypass the plan's python bookkeeping: if a batch was prefetched the current slot is armed on the
         # device under a key no tensor can match -- any eager use of the plan re-plans
@@ -555,11 +569,11 @@ class FusedTrainer:
         self._x32_key = g._key(next_ids) if tail else None
         self.graph = gr
         self.ctx.step_done()
-        return s["loss"]
+        return self._static["loss"]
 
-    def _capture(self, key):
-        head, tail = key
-        s, g = self._static, self.m.group
+    def _capture(self, key, s):
+        head, tail = key[:2]
+        g = self.m.group
         if not self._warm:          # allocator / lazy init warm-up, outside any capture
             assert head, "the first step of a trainer always pulls up front"
             side = torch.cuda.Stream(device=self.device)
@@ -580,9 +594,7 @@ class FusedTrainer:
         with torch.cuda.graph(gr):
             loss = self.m.forward_backward(s["ids"], s["dense"], s["labels"], next_ids=s["next_ids"] if tail else None,
                                            pulled=not head)
-        s.setdefault("loss", loss)
-        if loss.data_ptr() != s["loss"].data_ptr():
-            s["loss"] = loss
+        self._static["loss"] = loss          # the model's own loss buffer: the same tensor in every variant
         if getattr(g, "v2", False):
             g._armed = saved            # capture only recorded launches: the device-side slots are untouched
         self._graphs[key] = gr

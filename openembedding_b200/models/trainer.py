@@ -207,7 +207,10 @@ class _Pipeline:
         if j >= self.NBUF:
             self.done[i].synchronize()                        # loss_host[i] of batch j - NBUF has landed
         d = self.dev[i]
-        if next_ids is not None:
+        if next_ids is not None and getattr(self.t, "supports_stable_inputs", False):
+            # this pipeline's device buffers live as long as the pipeline and are refilled in place
+            loss = self.t.step(d["ids"], d["dense"], d["labels"], next_ids=next_ids, stable=True)
+        elif next_ids is not None:
             loss = self.t.step(d["ids"], d["dense"], d["labels"], next_ids=next_ids)
         else:
             loss = self.t.step(d["ids"], d["dense"], d["labels"])

@@ -75,7 +75,7 @@ def test_prefetch_next_batch_matches_plain(cuda_context, graph):
     vocab = [1000, 50, 20000, 7, 3000] + [300] * 21
     B = 256
     curves = []
-    for prefetch in (False, True):
+    for prefetch in (False, True, "stable"):
         reset_context()
         ctx = get_context()
         m = FusedCTR(vocab, embedding_dim=16, model="deepfm", batch=B, cache_threshold=64, lr=0.05,
@@ -90,12 +90,15 @@ def test_prefetch_next_batch_matches_plain(cuda_context, graph):
                 nxt = batches[order[k + 1]][0]
             if prefetch and k == 6:                               # announce one batch, train another: plan is dropped
                 nxt = batches[0][0]
-            losses.append(float(tr.step(*batches[i], next_ids=nxt)))
+            # "stable": the batches are resident tensors at fixed addresses -> graphs captured directly on them
+            losses.append(float(tr.step(*batches[i], next_ids=nxt, stable=prefetch == "stable")))
         torch.cuda.synchronize()
         ctx.backend.engine.check()
+        if prefetch == "stable" and graph:
+            assert len(tr._stable) >= 3, tr._stable.keys()
         curves.append(losses)
-    for a, b in zip(*curves):
-        assert abs(a - b) < 2e-4, curves
+    for a, b, c in zip(*curves):
+        assert abs(a - b) < 2e-4 and abs(a - c) < 2e-4, curves
 
 
 @pytest.mark.parametrize("cfg", [{"category": "adam", "learning_rate": 0.01},
