@@ -105,6 +105,7 @@ class CIN(nn.Module):
     def __init__(self, num_fields, layer_sizes=(128, 128), split_half=True, tc=False):
         super().__init__()
         _, Conv = _gemm_layers(tc)
+        self.tc = tc
         self.split_half = split_half
         self.layer_sizes = layer_sizes
         self.convs = nn.ModuleList()
@@ -121,6 +122,21 @@ class CIN(nn.Module):
 
     def forward(self, x):                      # x [B, F, D]
         B, Fn, D = x.shape
+        if self.tc and x.is_cuda:
+            # own kernels (ops/cin.py): rows = (sample, embedding column); the interaction tensor is written once as
+            # the bf16 operand of the tcgen05 GEMM, bias + relu in its epilogue; no transposes between layers
+            from ..ops.cin import cin_layer
+            xr = x.transpose(1, 2).reshape(B * D, Fn).contiguous().float()
+            hidden, outs = xr, []
+            for i, conv in enumerate(self.convs):
+                z = cin_layer(hidden, xr, conv.lin.weight, conv.lin.bias, relu=True)        # [B*D, size]
+                if self.split_half and i != len(self.convs) - 1:
+                    half = z.shape[1] // 2
+                    hidden, direct = z[:, :half], z[:, half:]
+                else:
+                    hidden, direct = z, z
+                outs.append(direct.reshape(B, D, -1).sum(1))
+            return torch.cat(outs, dim=1)      # [B, total]
         hidden, outs = x, []
         for i, conv in enumerate(self.convs):
             z = torch.einsum("bhd,bmd->bhmd", hidden, x).reshape(B, -1, D)

@@ -194,6 +194,7 @@ class FusedCTR:
         self._ar = None
         self._rider = False
         self.overlap = os.environ.get("EXB_OVERLAP", "0") == "1"
+        self.late_cachegrad = os.environ.get("EXB_LATE_CACHEGRAD", "0") == "1"     # measured: no gain (0.2260 vs 0.2240), the tail pull owns the SMs
         if ctx.world > 1:     # gradients are produced straight into the peer-mapped all-reduce buffer
             from ..ops.p2p_allreduce import P2PAllReduce
             self._ar = P2PAllReduce(ctx, off)
@@ -406,19 +407,23 @@ class FusedCTR:
                           splits=self.dw_splits, stream=st)
                 continue
             G.gemm_nt(self.dZT[l], prevT, self.Hp[l], dims[l], B, gW, mode=G.EPI_DW, splits=self.dw_splits, stream=st)
-        if self.nc:
+        def cachegrad():
             _ck(lib.exb_cachegrad(self.G32.data_ptr(), self.XS, self.ns * self.Dp, self.Dp, ids.data_ptr(), self.nf,
                                   self.cache_col.data_ptr(), self.cache_off.data_ptr(), self.nc,
                                   self.gview("cache_emb").data_ptr(), B, self.dlogit.data_ptr(),
                                   self.gview("cache_lin").data_ptr() if row_head else 0,
                                   self.cache_vocab.data_ptr(), st), "cachegrad")
+        tail = update and next_ids is not None and not forked
+        # one GPU: the gradients of the replicated tables are only needed by the dense optimizer, so their kernel moves
+        # behind push+update, next to the tail pull (several GPUs: the push kernel all-reduces them, they come first)
+        late_cg = bool(self.nc) and tail and self._ar is None and self.late_cachegrad
+        if self.nc and not late_cg:
+            cachegrad()
         self._mark("dw_gemm+cachegrad")
-        tail = False
         if update:
             if not forked:
                 self.group.push_update(ids, self.G32)
                 self._mark("push_update")
-            tail = next_ids is not None and not forked
             if tail:      # next batch: rows into X32 (free since the dX1 GEMM) + plan, beside the dense optimizer
                 cur = torch.cuda.current_stream(self.dev)
                 self._ev_fork.record(cur)
@@ -433,6 +438,8 @@ class FusedCTR:
             if self._ar is not None and not self._rider:
                 self._ar()
                 self._mark("allreduce")
+            if late_cg:
+                cachegrad()
             _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
             self._mark("optimizer")
             if forked:

@@ -178,6 +178,41 @@ def test_tc_linear_matches_torch(M, K, N):
     close(tc.bias.grad, ref.bias.grad, "db")
 
 
+@pytest.mark.parametrize("B,Fn,D,layers,split", [(64, 26, 9, (128, 128), True), (50, 7, 16, (32, 16, 8), True),
+                                                 (33, 5, 4, (24,), False)])
+def test_cin_own_kernels_match_torch(B, Fn, D, layers, split):
+    """xDeepFM CIN on own kernels (interaction written as the GEMM operand + tcgen05 GEMM with bias/relu + row-wise
+    backward, ops/cin.py) vs the einsum + Conv1d definition in fp32: output and every gradient"""
+    from openembedding_b200.models.ctr import CIN
+    torch.manual_seed(1)
+    ref = CIN(Fn, layers, split_half=split, tc=False).cuda()
+    own = CIN(Fn, layers, split_half=split, tc=True).cuda()
+    for cr, co in zip(ref.convs, own.convs):
+        with torch.no_grad():
+            # pre-activations far from zero (half of the channels on, half off): a relu whose input sits within the
+            # bf16 rounding error of zero flips between the two implementations and moves a whole gradient term
+            cr.bias.copy_(torch.where(torch.arange(cr.bias.numel(), device="cuda") % 2 == 0, 4.0, -4.0))
+            co.lin.weight.copy_(cr.weight.squeeze(-1))
+            co.lin.bias.copy_(cr.bias)
+    x = torch.randn(B, Fn, D, device="cuda") * 0.5
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y1, y2 = ref(x1), own(x2)
+    assert y1.shape == y2.shape == (B, ref.out_dim)
+    g = torch.randn_like(y1)
+    y1.backward(g)
+    y2.backward(g)
+    torch.cuda.synchronize()
+
+    def close(a, b, what):
+        err = float((a - b).abs().max())
+        assert err < 0.03 * float(b.abs().max()) + 1e-2, (what, err, float(b.abs().max()))
+    close(y2, y1, "y")
+    close(x2.grad, x1.grad, "dx")
+    for i, (cr, co) in enumerate(zip(ref.convs, own.convs)):
+        close(co.lin.weight.grad, cr.weight.grad.squeeze(-1), "dw%d" % i)
+        close(co.lin.bias.grad, cr.bias.grad, "db%d" % i)
+
+
 def test_cluster_multicast_variant_matches(monkeypatch):
     """EXB_GEMM_MC: the A tile is loaded once per cluster and multicast into the CTAs that share it"""
     import subprocess, sys, os
