@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(CIN_WARPS * 32) exb_cin_outer_kernel(const voi
 }
 
 // one warp per row r:  dhid[r, h] = sum_j dZ[r, h*m + j] * x[r, j],   dx[r, j] = sum_h dZ[r, h*m + j] * hid[r, h]
+// The dZ row is staged in shared memory AS bf16 (16-byte copies, no conversion pass): both reductions then read 2-byte
+// elements -- lane h walks m consecutive elements (word stride m/2 between lanes: odd for the usual even m = 26, so no
+// bank conflicts), lane j reads element h*m + j (consecutive lanes, consecutive elements).
 __global__ void __launch_bounds__(CIN_WARPS * 32) exb_cin_outer_bwd_kernel(const __nv_bfloat16* dZ, long long ldz,
                                                                             const void* hid, int hid_bf16, long long ld_hid, int H,
                                                                             const float* x, long long ld_x, int m,
@@ -72,36 +75,35 @@ __global__ void __launch_bounds__(CIN_WARPS * 32) exb_cin_outer_bwd_kernel(const
     exb::pdl_trigger();
     exb::pdl_wait();
     extern __shared__ __align__(16) unsigned char cin_smem[];
+    __shared__ float s_hx[CIN_WARPS][CIN_MAX_H + CIN_MAX_M];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = H * m;
     const int Cp = (C + 7) & ~7;
-    float* s_dz = reinterpret_cast<float*>(cin_smem) + (size_t)warp * (Cp + CIN_MAX_H + CIN_MAX_M);
-    float* s_h = s_dz + Cp;
+    __nv_bfloat16* s_dz = reinterpret_cast<__nv_bfloat16*>(cin_smem) + (size_t)warp * Cp;
+    float* s_h = s_hx[warp];
     float* s_x = s_h + CIN_MAX_H;
     for (int r = blockIdx.x * CIN_WARPS + warp; r < R; r += gridDim.x * CIN_WARPS) {
         const __nv_bfloat16* zr = dZ + (size_t)r * ldz;
-        for (int c0 = lane * 8; c0 < Cp; c0 += 32 * 8) {
-            const uint4 q = *reinterpret_cast<const uint4*>(zr + c0);
-            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(p2[k]);
-                s_dz[c0 + 2 * k] = f.x;
-                s_dz[c0 + 2 * k + 1] = f.y;
-            }
-        }
+        for (int c0 = lane * 8; c0 < Cp; c0 += 32 * 8)
+            *reinterpret_cast<uint4*>(s_dz + c0) = *reinterpret_cast<const uint4*>(zr + c0);
         for (int h = lane; h < H; h += 32) s_h[h] = load_as_float(hid, hid_bf16, (size_t)r * ld_hid + h);
         for (int j = lane; j < m; j += 32) s_x[j] = x[(size_t)r * ld_x + j];
         __syncwarp();
         for (int h = lane; h < H; h += 32) {
+            const __nv_bfloat16* p = s_dz + h * m;
             float a = 0.f;
-            for (int j = 0; j < m; ++j) a += s_dz[h * m + j] * s_x[j];
+            for (int j = 0; j < m; ++j) a += __bfloat162float(p[j]) * s_x[j];
             dhid[(size_t)r * ld_dhid + h] = a;
         }
         for (int j = lane; j < m; j += 32) {
-            float a = 0.f;
-            for (int h = 0; h < H; ++h) a += s_dz[h * m + j] * s_h[h];
-            dx[(size_t)r * ld_dx + j] = a;
+            float a0 = 0.f, a1 = 0.f;
+            int h = 0;
+            for (; h + 1 < H; h += 2) {
+                a0 += __bfloat162float(s_dz[h * m + j]) * s_h[h];
+                a1 += __bfloat162float(s_dz[(h + 1) * m + j]) * s_h[h + 1];
+            }
+            if (h < H) a0 += __bfloat162float(s_dz[h * m + j]) * s_h[h];
+            dx[(size_t)r * ld_dx + j] = a0 + a1;
         }
         __syncwarp();
     }
@@ -131,7 +133,7 @@ int exb_cin_outer_bwd(uint64_t dZ, long long ldz, uint64_t hid, int hid_bf16, lo
     if (H > CIN_MAX_H || m > CIN_MAX_M || H < 1 || m < 1) { g_cin_err = "cin_outer_bwd: H <= 256, m <= 64"; return -1; }
     const int C = H * m, Cp = (C + 7) & ~7;
     if (ldz % 8 || Cp > ldz) { g_cin_err = "cin_outer_bwd: dZ rows must be 16-byte aligned and hold H*m columns"; return -1; }
-    const size_t smem = (size_t)CIN_WARPS * (Cp + CIN_MAX_H + CIN_MAX_M) * sizeof(float);
+    const size_t smem = (size_t)CIN_WARPS * Cp * sizeof(__nv_bfloat16);
     if (smem > 200 * 1024) { g_cin_err = "cin_outer_bwd: H*m too large for the shared-memory row buffers"; return -1; }
     static size_t attr = 0;
     if (smem > attr) {

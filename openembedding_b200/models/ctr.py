@@ -99,6 +99,25 @@ def _gemm_layers(tc):
     return nn.Linear, lambda cin, cout: nn.Conv1d(cin, cout, 1)
 
 
+class _GatherRows(torch.autograd.Function):
+    """``weight[idx]`` for the small replicated ("cache") tables whose backward is an atomic ``index_add_`` instead of
+    ``embedding_dense_backward``'s radix sort of all indices (8 sort passes + a segmented reduction per table group:
+    ~170 us of a step at batch 4096 x 11 cached features)"""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        ctx.save_for_backward(idx)
+        ctx.rows = weight.shape[0]
+        return weight.index_select(0, idx.reshape(-1)).reshape(tuple(idx.shape) + (weight.shape[1],))
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        gw = torch.zeros((ctx.rows, g.shape[-1]), dtype=g.dtype, device=g.device)
+        gw.index_add_(0, idx.reshape(-1), g.reshape(-1, g.shape[-1]))
+        return gw, None
+
+
 class CIN(nn.Module):
     """Compressed Interaction Network (xDeepFM), DeepCTR defaults: split_half, relu."""
 
@@ -249,8 +268,8 @@ class CTRModel(nn.Module):
         if self.cached:
             cid = ids[:, self.cache_cols] + self.cache_offsets            # [B, nc]
             if self.has_emb:
-                embs.append(F.embedding(cid, self.cache_emb))
-            lins.append(F.embedding(cid, self.cache_lin).squeeze(-1))
+                embs.append(_GatherRows.apply(self.cache_emb, cid))
+            lins.append(_GatherRows.apply(self.cache_lin, cid).squeeze(-1))
         linear = torch.cat(lins, dim=1).sum(dim=1)
         if self.dense_linear is not None:
             linear = linear + self.dense_linear(dense).squeeze(-1)
