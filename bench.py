@@ -152,7 +152,7 @@ def run_baseline(a, torch, dist, world, rank, local_rank):
     ms = e0.elapsed_time(e1)
     loss_val = float(loss)
     pipe = HostPipeline(model, a.batch, len(vocab), 13)
-    for s in range(max(3 * pipe.NBUF, a.warmup // 2)):      # every (buffer i -> buffer i+1) graph variant exists before timing
+    for s in range(max(3 * getattr(pipe, "NBUF", 1), a.warmup // 2)):      # every (buffer i -> buffer i+1) graph variant exists before timing
         pipe.submit(*host[s % a.pool])
     pipe.last_loss()
     sync_all()
@@ -292,7 +292,7 @@ def main():
 
     # ---------------- end-to-end through the public pipeline API: pinned H2D in, loss D2H out, every step
     pipe = trainer.make_pipeline(a.batch, len(vocab), 13)
-    for s in range(max(3 * pipe.NBUF, a.warmup // 2)):      # every (buffer i -> buffer i+1) graph variant exists before timing
+    for s in range(max(3 * getattr(pipe, "NBUF", 1), a.warmup // 2)):      # every (buffer i -> buffer i+1) graph variant exists before timing
         pipe.submit(*host[s % a.pool])
     pipe.last_loss()
     sync_all()
