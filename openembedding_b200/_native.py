@@ -70,6 +70,7 @@ def core():
                                        i32p, i32p, u64p, u64p])
         P(lib, "exb_fr_block_size", c_int64, [c_void_p])
         P(lib, "exb_fr_block", c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p, c_uint64])
+        P(lib, "exb_fr_skip_block", c_int, [c_void_p, c_uint64, c_uint64, c_uint64])
         P(lib, "exb_fr_close", None, [c_void_p])
         P(lib, "exb_unique_indices", c_uint64, [c_void_p, c_uint64, c_void_p, c_void_p])
         _core = lib
@@ -104,6 +105,8 @@ def cuda():
         P(lib, "exb_table_info", c_int, [c_void_p, c_int, u64p])
         P(lib, "exb_table_set_peer", c_int, [c_void_p, c_int, c_int, c_uint64, c_uint64])
         P(lib, "exb_engine_commit", c_int, [c_void_p])
+        P(lib, "exb_engine_accept_ctx", c_int, [c_void_p])
+        P(lib, "exb_engine_ctx_version", c_uint32, [c_void_p])
         P(lib, "exb_table_size", c_int, [c_void_p, c_int, u64p])
         P(lib, "exb_table_enumerate", c_int, [c_void_p, c_int, c_uint64, c_uint64, u64p, c_uint64])
         P(lib, "exb_table_gather", c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64])

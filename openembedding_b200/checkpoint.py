@@ -130,8 +130,9 @@ def _save_model_local(ctx, path, include_optimizer=True, num_files=None, persist
     ctx.barrier()
 
 
-def iter_shard_file(path):
-    """yield ('header', dict) then ('block', indices, weights, states) records of one file."""
+def iter_shard_file(path, want=None):
+    """yield ('header', dict) then ('block', hdr, global ids, weights, states) records of one file. ``want(hdr)`` False:
+    the segment's blocks are seeked past, not read (a rank that does not own the segment's shard)."""
     lib = _native.core()
     r = lib.exb_fr_open(path.encode())
     if not r:
@@ -157,10 +158,16 @@ def iter_shard_file(path):
             np_dt = np.float32 if hdr["dtype"] == "float32" else np.float64
             itemsize = np.dtype(np_dt).itemsize
             done = 0
+            skip = want is not None and not want(hdr)
             while done < hdr["num_items"]:
                 n = lib.exb_fr_block_size(r)
                 if n < 0:
                     raise IOError("truncated shard file " + path)
+                if skip:
+                    if lib.exb_fr_skip_block(r, n, n * hdr["dim"] * itemsize, n * hdr["state_line_size"]) != 0:
+                        raise IOError("truncated shard file " + path)
+                    done += n
+                    continue
                 idx = np.empty(n, dtype=np.uint64)
                 w = np.empty((n, hdr["dim"]), dtype=np_dt)
                 scols = hdr["state_line_size"] // itemsize
@@ -185,7 +192,13 @@ def load_model(ctx, path, restore_config_only=False):
 
 
 def _load_model_local(ctx, path, restore_config_only=False):
-    """Collective: every rank scans every file and keeps the rows it owns (re-shard)."""
+    """Collective. Every rank walks the segment headers of every file, but reads only the segments it can own: a
+    segment holds ONE saved shard (ids with ``id % shard_num == shard_id``), so with an unchanged ``shard_num`` its
+    owner in the current layout is the single rank ``(shard_base + shard_id) % world`` -- whatever the world size was
+    at save time -- and everybody else seeks past it. Only a changed ``shard_num`` (impossible today: the model meta
+    must match) falls back to reading everything and filtering row by row (``load_rows``). ``restore_config_only``:
+    initializer / optimizer configs are restored, no rows are loaded (reference: ``load_model`` with only the
+    variable configs, used before a ``restore`` from the persistent tier)."""
     meta = read_model_meta(path)
     mine = model_meta_dict(ctx)["variables"]
     if meta["variables"] != mine:
@@ -202,10 +215,18 @@ def _load_model_local(ctx, path, restore_config_only=False):
         sdir = os.path.join(path, str(st.storage_id))
         if not os.path.isdir(sdir):
             continue
+        def want(hdr, st=st):
+            if restore_config_only:
+                return False
+            var = st.variables[hdr["variable_id"]]
+            if int(hdr["shard_num"]) != int(var.shard_num):
+                return True                      # re-sharded by id: every rank filters row by row
+            return (int(var.shard_base) + int(hdr["shard_id"])) % ctx.world == ctx.rank
+
         for fn in sorted(os.listdir(sdir)):
             if not fn.startswith("model_"):
                 continue
-            for rec in iter_shard_file(os.path.join(sdir, fn)):
+            for rec in iter_shard_file(os.path.join(sdir, fn), want):
                 if rec[0] == "header":
                     hdr = rec[1]
                     var = st.variables[hdr["variable_id"]]

@@ -408,6 +408,13 @@ int exb_fr_header(void* h, uint32_t* variable_id, int32_t* dtype, uint64_t* dim,
 int64_t exb_fr_block_size(void* h) {
     uint64_t n; if (fread(&n, 8, 1, ((FileReader*)h)->f) != 1) return -1; return (int64_t)n;
 }
+// skip a block of n rows (after exb_fr_block_size) without reading it: the loader of a rank that does not own the
+// segment's shard seeks past it
+int exb_fr_skip_block(void* h, uint64_t n, uint64_t wbytes, uint64_t sbytes) {
+    FILE* f = ((FileReader*)h)->f;
+    const uint64_t total = n * 8 + wbytes + sbytes;
+    return fseeko(f, (off_t)total, SEEK_CUR) == 0 ? 0 : -1;
+}
 int exb_fr_block(void* h, uint64_t n, uint64_t* indices, void* weights, uint64_t wbytes, void* states,
                  uint64_t sbytes) {
     FILE* f = ((FileReader*)h)->f;

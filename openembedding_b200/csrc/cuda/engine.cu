@@ -31,6 +31,9 @@ namespace {
 
 const size_t SYNC_BYTES = 2u << 20;
 const size_t OFF_FLAGS = 0, OFF_EPOCH = 128, OFF_STATUS = 132, OFF_GBAR = 136, OFF_STATS = 256;
+// context versions (exb_common.cuh: ctx_check): [64, 96) announced by every rank's host into this block, [96, 128) the
+// versions this rank's mappings were built against (accepted at the last connect)
+const size_t OFF_CTX_ANNOUNCED = 4 * EXB_CTX_ANNOUNCED_WORD, OFF_CTX_EXPECTED = 4 * EXB_CTX_EXPECTED_WORD;
 
 struct HostTable {
     TableDev d;
@@ -48,6 +51,7 @@ struct Engine {
     size_t d_tables_cap = 0;
     char* sync_local = nullptr;
     char* sync_peer[EXB_MAX_PEERS] = {nullptr};
+    unsigned ctx_version = 1;   // bumped whenever a table slab of this rank moves (alloc, rehash): peers' mappings are stale
 };
 
 struct Plan {
@@ -64,6 +68,28 @@ struct Plan {
 
 int pow2_ceil_int(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Context versioning (reference: pico-ps ctx version, Status SERVER_TOO_{NEW,OLD}_CTX): a rank announces its version
+// into its own sync block and into every peer's (mapped) block; kernels compare the announced versions with the ones
+// accepted at the last connect and raise EXB_ERR_CTX_VERSION on a mismatch (a peer moved a slab, this rank still
+// holds the old mapping).
+cudaError_t announce_ctx(Engine* e, int only_peer = -1) {
+    for (int r = 0; r < e->world; ++r) {
+        if (only_peer >= 0 && r != only_peer) continue;
+        char* base = e->sync_peer[r];
+        if (!base) continue;
+        cudaError_t err = cudaMemcpy(base + OFF_CTX_ANNOUNCED + 4 * e->rank, &e->ctx_version, 4, cudaMemcpyDefault);
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+cudaError_t bump_ctx(Engine* e) {
+    ++e->ctx_version;
+    return announce_ctx(e);
+}
+cudaError_t accept_own_ctx(Engine* e) {
+    return cudaMemcpy(e->sync_local + OFF_CTX_EXPECTED + 4 * e->rank, &e->ctx_version, 4, cudaMemcpyHostToDevice);
+}
 
 // ------------------------------------------------------------ utility kernels
 __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long n, unsigned long long v) {
@@ -324,6 +350,7 @@ void* exb_engine_create(int device, int rank, int world) {
     CKP(cudaMemset(e->sync_local, 0, SYNC_BYTES));
     for (int i = 0; i < EXB_MAX_PEERS; ++i) e->sync_peer[i] = nullptr;
     e->sync_peer[rank] = e->sync_local;
+    if (announce_ctx(e) != cudaSuccess || accept_own_ctx(e) != cudaSuccess) { fail_msg("engine: context version"); return nullptr; }
     return e;
 }
 void exb_engine_destroy(void* h) {
@@ -344,7 +371,22 @@ int exb_engine_sms(void* h) { return ((Engine*)h)->sms; }
 void exb_engine_set_max_ctas(void* h, int n) { ((Engine*)h)->max_ctas = n; }
 uint64_t exb_engine_sync_ptr(void* h) { return (uint64_t)((Engine*)h)->sync_local; }
 uint64_t exb_engine_sync_bytes() { return SYNC_BYTES; }
-void exb_engine_set_peer_sync(void* h, int peer, uint64_t ptr) { ((Engine*)h)->sync_peer[peer] = (char*)ptr; }
+void exb_engine_set_peer_sync(void* h, int peer, uint64_t ptr) {
+    Engine* e = (Engine*)h;
+    e->sync_peer[peer] = (char*)ptr;
+    cudaSetDevice(e->device);
+    announce_ctx(e, peer);       // the newly mapped peer learns this rank's current context version
+}
+// accept every rank's announced context version as the one this rank's mappings are built against. Collective
+// protocol (ops/sparse_engine.py: connect): all ranks have exchanged their mappings, a barrier, then this call.
+int exb_engine_accept_ctx(void* h) {
+    Engine* e = (Engine*)h;
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(e->sync_local + OFF_CTX_EXPECTED, e->sync_local + OFF_CTX_ANNOUNCED, 4 * EXB_MAX_PEERS, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+unsigned exb_engine_ctx_version(void* h) { return ((Engine*)h)->ctx_version; }
 
 // returns 0 and the error status word (device sync!)
 int exb_engine_status(void* h, int* status, uint64_t* stats16) {
@@ -419,6 +461,7 @@ int exb_table_alloc(void* h, int ti) {
     HostTable& t = e->tables[ti];
     CK(cudaSetDevice(e->device));
     if (t.allocated) return 0;
+    CK(bump_ctx(e));
     layout_table(t.d);
     t.w_bytes = align_up((size_t)t.d.rows * t.d.wstride * sizeof(float), 2u << 20);
     CK(cudaMalloc(&t.w_local, t.w_bytes));
@@ -463,6 +506,7 @@ int exb_table_set_peer(void* h, int ti, int peer, uint64_t w_ptr, uint64_t keys_
 int exb_engine_commit(void* h) {
     Engine* e = (Engine*)h;
     CK(cudaSetDevice(e->device));
+    CK(accept_own_ctx(e));        // the device table descriptors are refreshed below: this rank's own view is current
     return upload_tables(e);
 }
 int exb_table_size(void* h, int ti, uint64_t* out) {
@@ -563,6 +607,7 @@ int exb_table_rehash(void* h, int ti, uint64_t new_capacity) {
     for (int p = 0; p < EXB_MAX_PEERS; ++p)
         if (p != e->rank) { n.d.w[p] = nullptr; n.d.keys[p] = nullptr; }
     t = n;
+    CK(bump_ctx(e));              // peers still map the freed slabs: their kernels must notice until they reconnect
     return 0;
 }
 

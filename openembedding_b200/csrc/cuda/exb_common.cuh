@@ -104,7 +104,11 @@ enum ExbStatus : int {
     EXB_ERR_HASH_FULL = 3,
     EXB_ERR_INBOX_OVERFLOW = 4,
     EXB_ERR_CMAP_FULL = 5,
+    EXB_ERR_CTX_VERSION = 6,     // a rank announced a newer context (moved a slab) than this rank's mappings were built for
 };
+// u32 word offsets inside a rank's sync block (PlanDev::flags[rank] points at its start)
+#define EXB_CTX_ANNOUNCED_WORD 16
+#define EXB_CTX_EXPECTED_WORD 24
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
@@ -279,6 +283,18 @@ __device__ __forceinline__ void peer_barrier(const PlanDev& P, bool wait = true)
     __syncthreads();
     if (threadIdx.x == 0) *(volatile unsigned*)P.epoch = e;
     __syncthreads();
+}
+
+// Context-version guard (engine.cu: announce_ctx / exb_engine_accept_ctx), first thing in every plan kernel: the versions
+// the ranks have announced into this rank's sync block must be the ones this rank's peer mappings were built against.
+// Local loads only (two words per rank, CTA 0).
+__device__ __forceinline__ void ctx_check(const PlanDev& P) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < P.W) {
+        const unsigned* blk = P.flags[P.rank];
+        const unsigned announced = ld_relaxed_sys_u32(blk + EXB_CTX_ANNOUNCED_WORD + threadIdx.x);
+        const unsigned expected = ld_relaxed_sys_u32(blk + EXB_CTX_EXPECTED_WORD + threadIdx.x);
+        if (announced != expected) set_error(P.status, EXB_ERR_CTX_VERSION);
+    }
 }
 
 // Every CTA of a kernel that reads peer shards: wait until all peers have signalled the

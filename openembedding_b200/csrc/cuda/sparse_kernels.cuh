@@ -298,6 +298,7 @@ exb_pull_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);   // descriptors are written by the host only
     pdl_wait();
+    ctx_check(P);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -740,6 +741,7 @@ exb_push_update_kernel(const TableDev* __restrict__ tables, PlanDev P,
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
     pdl_wait();
+    ctx_check(P);
     int* s_prefix = S.seg_prefix;
     const int wic = threadIdx.x >> 5;
     unsigned char* stage_end = exb_smem + exb_smem_bytes(P.PT, P.F, true);

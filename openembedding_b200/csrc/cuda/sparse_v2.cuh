@@ -113,6 +113,7 @@ exb_plan_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long*
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
     pdl_wait();
+    ctx_check(P);
     const SlotDev L = pick_slot(P, which);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -140,6 +141,7 @@ exb_pull_plan_kernel(const TableDev* __restrict__ tables, PlanDev P, const long 
     const SmemView S = stage_plan(tables, P, exb_smem);
     PP_STAMP(1);
     pdl_wait();
+    ctx_check(P);
     PP_STAMP(2);
     const SlotDev L = pick_slot(P, which);
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -314,6 +316,7 @@ exb_pull2_kernel(const TableDev* __restrict__ tables, PlanDev P, const long long
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
     pdl_wait();
+    ctx_check(P);
     const SlotDev L = pick_slot(P, which);
     int* s_prefix = S.seg_prefix;
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -407,6 +410,7 @@ exb_push2_kernel(const TableDev* __restrict__ tables, PlanDev P, const float* __
     pdl_trigger();
     const SmemView S = stage_plan(tables, P, exb_smem);
     pdl_wait();
+    ctx_check(P);
     const SlotDev L = pick_slot(P, which);
     int* s_prefix = S.seg_prefix;
     const int wic = threadIdx.x >> 5;

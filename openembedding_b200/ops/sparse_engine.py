@@ -18,6 +18,7 @@ from ..status import ENGINE_STATUS, Status, StatusError
 _STATUS_TEXT = {
     0: "ok", 1: "grid barrier timeout", 2: "peer barrier timeout (a rank did not arrive)",
     3: "hash table full (grow it)", 4: "inbox overflow", 5: "combine map full",
+    6: "context version mismatch: a rank moved a table slab (alloc / rehash) after the last connect()",
 }
 
 
@@ -146,6 +147,9 @@ class CudaEngine:
                 plan.connected = True
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)
+        # every rank has mapped every slab and announced its context version: these are the versions the kernels
+        # will insist on (ctx_check) until the next connect
+        _native.cuda_check(self.lib.exb_engine_accept_ctx(self.h), "accept_ctx")
 
     @staticmethod
     def connect_local(engines):
@@ -172,6 +176,8 @@ class CudaEngine:
             for plan in e.plans:
                 _native.cuda_check(e.lib.exb_plan_commit(plan.h), "plan_commit")
                 plan.connected = True
+        for e in engines:
+            _native.cuda_check(e.lib.exb_engine_accept_ctx(e.h), "accept_ctx")
 
     # ---------------------------------------------------------------- plans
     def make_plan(self, feat_tables, batch, feat_offsets=None, io_stride=None, feat_cols=None, ncols=None,

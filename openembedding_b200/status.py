@@ -9,9 +9,11 @@ Here the training data plane is a set of kernels: a failed verb leaves a device-
 code (``csrc/cuda/exb_common.cuh: ExbStatus``) that ``CudaEngine.check()`` (blocking) and
 ``CudaEngine.poll()`` (asynchronous read-back, called every step by ``CudaBackend.tick``) turn into
 ``StatusError``; the serving client maps transport failures to NO_REPLICA / TIMEOUT and retries
-(``serving/client.py``). ``SERVER_TOO_*_CTX`` has no counterpart in training (no server processes
-whose table context could lag); in serving the equivalent is a stale placement record, refreshed
-from the master tree on every failed pull.
+(``serving/client.py``). Context versions: every rank announces a version word into its peers' sync blocks whenever
+one of its table slabs moves (alloc, rehash); every plan kernel compares the announced versions with the ones accepted
+at the last collective connect (``exb_common.cuh: ctx_check``) and raises ``SERVER_TOO_OLD_CTX`` -- retryable after
+``CudaEngine.connect()``. In serving the equivalent is a stale placement record, refreshed from the master tree on
+every failed pull.
 """
 import enum
 
@@ -50,6 +52,7 @@ ENGINE_STATUS = {
     3: Status.OOM,            # hash table full
     4: Status.OOM,            # inbox overflow
     5: Status.OOM,            # combine map full
+    6: Status.SERVER_TOO_OLD_CTX,   # a peer moved a table slab (rehash / alloc): this rank's mappings are stale -> reconnect
 }
 
 

@@ -190,3 +190,45 @@ def test_checkpoint_multiple_dump_files_and_optimizer_change(cpu_context):
     finally:
         oe.flags.config = old
         reset_context()
+
+
+def test_load_skips_foreign_segments_and_config_only(cpu_context):
+    """a loader reads only the segments whose shard it owns (the others are seeked past); restore_config_only restores
+    initializer / optimizer configs without loading a row"""
+    import openembedding_b200.torch as embed
+    from openembedding_b200 import _native, checkpoint
+    from openembedding_b200.config import dump_variable_config
+    from openembedding_b200.context import get_context, reset_context
+    lib = _native.core()
+    d = tempfile.mkdtemp()
+    fn = d + "/model_0_0"
+    cfg = dump_variable_config("array", 0, {"category": "default"}, "zeros").encode()
+    w = lib.exb_fw_open(fn.encode())
+    for shard in range(3):                       # three segments (saved shards) in one file
+        local = np.arange(5, dtype=np.uint64)
+        rows = np.full((5, 2), float(shard), dtype=np.float32)
+        lib.exb_fw_header(w, 0, 0x104, 2, 100, cfg, len(cfg), shard, 3, 0, local.size)
+        lib.exb_fw_block(w, local.size, local.ctypes.data, rows.ctypes.data, rows.nbytes, None, 0)
+    lib.exb_fw_close(w)
+    recs = list(checkpoint.iter_shard_file(fn, want=lambda h: h["shard_id"] == 1))
+    assert [r[0] for r in recs] == ["header", "header", "block", "header"]
+    blk = [r for r in recs if r[0] == "block"][0]
+    assert blk[1]["shard_id"] == 1 and (blk[3] == 1.0).all() and list(blk[2]) == [1, 4, 7, 10, 13]
+    assert [r[0] for r in checkpoint.iter_shard_file(fn, want=lambda h: False)] == ["header"] * 3
+    assert sum(r[0] == "block" for r in checkpoint.iter_shard_file(fn)) == 3
+
+    reset_context()
+    ctx = get_context()
+    emb = embed.Embedding(50, 2, embeddings_initializer={"category": "constant", "value": 0.5})
+    opt = embed.distributed_optimizer(torch.optim.Adagrad(emb.parameters(), lr=0.1, initial_accumulator_value=0.1))
+    loss = (emb(torch.arange(10)) ** 2).sum()
+    opt.zero_grad(); loss.backward(); opt.step()
+    checkpoint.save_model(ctx, d + "/ck", include_optimizer=True)
+    reset_context()
+    ctx = get_context()
+    emb2 = embed.Embedding(50, 2, embeddings_initializer={"category": "constant", "value": 0.0})
+    checkpoint.load_model(ctx, d + "/ck", restore_config_only=True)
+    var = emb2.variable.variable
+    assert var.optimizer["category"] == "adagrad" and abs(var.optimizer["learning_rate"] - 0.1) < 1e-9
+    assert torch.equal(emb2(torch.arange(50)).detach(), torch.full((50, 2), 0.5))   # restored initializer, no rows
+    reset_context()

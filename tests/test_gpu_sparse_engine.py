@@ -259,6 +259,43 @@ def test_checkpoint_row_access_and_rehash():
     e.close()
 
 
+def test_context_version_guard():
+    """a rank that moves a table slab (rehash) announces a new context version; the peers' kernels report
+    SERVER_TOO_OLD_CTX until everybody has reconnected (reference: pico-ps ctx version / Status::SERVER_TOO_OLD_CTX)"""
+    from openembedding_b200.ops.sparse_engine import CudaEngine
+    from openembedding_b200.status import Status, StatusError
+    dev = torch.device("cuda", 0)
+    engines = [CudaEngine(0, r, 2, max_ctas=6) for r in range(2)]
+    for e in engines:
+        t = e.add_table(8, 0, True, capacity=1024)
+        e.set_initializer(t, UNIFORM, 0)
+        e.set_optimizer(t, ADAGRAD)
+        e.alloc(t)
+    plans = [e.make_plan([0], 128) for e in engines]
+    CudaEngine.connect_local(engines)
+    # even ids: owned by rank 0, so the pull below never dereferences rank 1's (freed) slabs
+    ids = (torch.arange(128, dtype=torch.int64) * 7919 * 2).reshape(-1, 1).to(dev)
+    before = plans[0].pull(ids).clone()
+    torch.cuda.synchronize()
+    engines[0].check()
+    v0 = engines[1].lib.exb_engine_ctx_version(engines[1].h)
+    engines[1].rehash(0, 4096)                      # rank 1 moves its slabs; rank 0 still maps the old ones
+    assert engines[1].lib.exb_engine_ctx_version(engines[1].h) == v0 + 1
+    plans[0].pull(ids)
+    torch.cuda.synchronize()
+    with pytest.raises(StatusError) as ei:
+        engines[0].check()
+    assert ei.value.status == Status.SERVER_TOO_OLD_CTX and ei.value.status.retryable
+    CudaEngine.connect_local(engines)               # the refresh: re-map, accept the new versions
+    after = plans[0].pull(ids)
+    torch.cuda.synchronize()
+    engines[0].check()
+    engines[1].check()
+    assert torch.equal(before, after)
+    for e in engines:
+        e.close()
+
+
 @pytest.mark.parametrize("world,dim,v2", [(1, 10, 1), (1, 65, 1), (2, 65, 1), (2, 17, 1), (1, 65, 0), (2, 65, 0), (2, 10, 0)])
 def test_split_row_feature(world, dim, v2, monkeypatch):
     """one table row [embedding(D) | linear(1)] feeding two places of the activation / gradient row"""
