@@ -71,6 +71,9 @@ def core():
         P(lib, "exb_fr_block_size", c_int64, [c_void_p])
         P(lib, "exb_fr_block", c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p, c_uint64])
         P(lib, "exb_fr_skip_block", c_int, [c_void_p, c_uint64, c_uint64, c_uint64])
+        P(lib, "exb_lz4_bound", c_int64, [c_int64])
+        P(lib, "exb_lz4_compress", c_int64, [c_char_p, c_int64, c_void_p, c_int64])
+        P(lib, "exb_lz4_decompress", c_int64, [c_char_p, c_int64, c_void_p, c_int64])
         P(lib, "exb_fr_close", None, [c_void_p])
         P(lib, "exb_unique_indices", c_uint64, [c_void_p, c_uint64, c_void_p, c_void_p])
         _core = lib

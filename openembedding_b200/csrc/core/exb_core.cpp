@@ -438,4 +438,75 @@ uint64_t exb_unique_indices(const uint64_t* ids, uint64_t n, uint64_t* out_uniqu
     return u;
 }
 
+// ---- LZ4 block codec (message / payload compression; the reference's RpcView / Compress offers snappy, lz4 and zlib,
+// pico-core/include/pico-core/Compress.h). Standard LZ4 block format: sequences of [token | literal length bytes |
+// literals | 2-byte offset | match length bytes]; greedy single-probe compressor with a 64 K-entry hash table.
+// The decompressor checks every bound: corrupt input yields -1, never an out-of-range access.
+int64_t exb_lz4_bound(int64_t n) { return n + n / 255 + 16; }
+
+static inline uint32_t lz4_read32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+int64_t exb_lz4_compress(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+    if (n < 0 || cap < exb_lz4_bound(n)) return -1;
+    const int HASH_LOG = 16;
+    std::vector<int64_t> table((size_t)1 << HASH_LOG, -1);
+    uint8_t* op = dst;
+    int64_t anchor = 0, ip = 0;
+    const int64_t mflimit = n - 12, matchlimit = n - 5;
+    auto emit_length = [&](int64_t len) { while (len >= 255) { *op++ = 255; len -= 255; } *op++ = (uint8_t)len; };
+    while (ip <= mflimit) {
+        const uint32_t seq = lz4_read32(src + ip);
+        const uint32_t h = (seq * 2654435761u) >> (32 - HASH_LOG);
+        const int64_t ref = table[h];
+        table[h] = ip;
+        if (ref < 0 || ip - ref > 65535 || lz4_read32(src + ref) != seq) { ++ip; continue; }
+        int64_t mlen = 4;
+        while (ip + mlen < matchlimit && src[ref + mlen] == src[ip + mlen]) ++mlen;
+        const int64_t lit = ip - anchor;
+        uint8_t* token = op++;
+        *token = (uint8_t)((lit >= 15 ? 15 : lit) << 4);
+        if (lit >= 15) emit_length(lit - 15);
+        memcpy(op, src + anchor, (size_t)lit); op += lit;
+        const uint16_t off = (uint16_t)(ip - ref);
+        *op++ = (uint8_t)(off & 255); *op++ = (uint8_t)(off >> 8);
+        const int64_t ml = mlen - 4;
+        *token |= (uint8_t)(ml >= 15 ? 15 : ml);
+        if (ml >= 15) emit_length(ml - 15);
+        ip += mlen;
+        anchor = ip;
+    }
+    const int64_t lit = n - anchor;       // last sequence: literals only
+    uint8_t* token = op++;
+    *token = (uint8_t)((lit >= 15 ? 15 : lit) << 4);
+    if (lit >= 15) emit_length(lit - 15);
+    memcpy(op, src + anchor, (size_t)lit); op += lit;
+    return (int64_t)(op - dst);
+}
+
+int64_t exb_lz4_decompress(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+    const uint8_t* ip = src; const uint8_t* const iend = src + n;
+    uint8_t* op = dst; uint8_t* const oend = dst + cap;
+    if (n <= 0) return n == 0 ? 0 : -1;
+    for (;;) {
+        if (ip >= iend) return -1;
+        const uint8_t token = *ip++;
+        int64_t lit = token >> 4;
+        if (lit == 15) { uint8_t b; do { if (ip >= iend) return -1; b = *ip++; lit += b; } while (b == 255); }
+        if (lit > iend - ip || lit > oend - op) return -1;
+        memcpy(op, ip, (size_t)lit); op += lit; ip += lit;
+        if (ip == iend) break;            // the last sequence carries no match
+        if (iend - ip < 2) return -1;
+        const int64_t off = ip[0] | (ip[1] << 8); ip += 2;
+        if (off == 0 || off > op - dst) return -1;
+        int64_t ml = token & 15;
+        if (ml == 15) { uint8_t b; do { if (ip >= iend) return -1; b = *ip++; ml += b; } while (b == 255); }
+        ml += 4;
+        if (ml > oend - op) return -1;
+        const uint8_t* m = op - off;
+        for (int64_t i = 0; i < ml; ++i) op[i] = m[i];     // overlapping copies are the format's run-length trick
+        op += ml;
+    }
+    return (int64_t)(op - dst);
+}
+
 }  // extern "C"

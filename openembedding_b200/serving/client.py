@@ -48,9 +48,12 @@ class ModelVariable:
 
 class ServingClient:
     def __init__(self, master_endpoint, policy="round_robin", message_compress=""):
-        """message_compress: "" or "zlib" (EnvConfig server.message_compress; snappy/lz4 are accepted by the
-        config checker for compatibility but fall back to zlib, the only codec in the image)."""
+        """message_compress: "", "zlib", "lz4" or "snappy" (EnvConfig server.message_compress; utils/compress.py: native
+        lz4 block codec, zlib; snappy is served by the lz4 codec)."""
         self.compress = bool(message_compress)
+        from ..utils import compress as _c
+        self._codec = _c
+        self._encoding = _c.encoding_of(message_compress) or "deflate"
         self.master = MasterClient(master_endpoint)
         self._rr = itertools.count()
         self.policy = policy
@@ -108,14 +111,15 @@ class ServingClient:
             try:
                 body, hdr = local_ids.tobytes(), {}
                 if self.compress:
-                    hdr["Accept-Encoding"] = "deflate"
+                    hdr["Accept-Encoding"] = self._encoding
                     if len(body) >= 4096:
-                        body, hdr["Content-Encoding"] = zlib.compress(body, 1), "deflate"
+                        body, hdr["Content-Encoding"] = self._codec.compress(body, self._encoding), self._encoding
                 req = urllib.request.Request(url, data=body, method="POST", headers=hdr)
                 with urllib.request.urlopen(req, timeout=max(0.5, timeout / 4)) as r:
                     data = r.read()
-                    if r.headers.get("Content-Encoding", "") == "deflate":
-                        data = zlib.decompress(data)
+                    enc = r.headers.get("Content-Encoding", "")
+                    if enc in ("deflate", "lz4"):
+                        data = self._codec.decompress(data, enc)
                 return np.frombuffer(data, dtype=np_dt).reshape(local_ids.size, dim)
             except Exception:
                 self._dead[nid] = time.time()         # handle_timeout: mark the node dead, retry elsewhere

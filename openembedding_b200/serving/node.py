@@ -22,6 +22,7 @@ import numpy as np
 from .. import _native
 from ..checkpoint import iter_shard_file, read_model_meta
 from ..config import DTYPES, initializer_params, load_variable_config, mix_seed
+from ..utils import compress as _compress
 from ..utils import log, metrics
 
 
@@ -70,11 +71,14 @@ class ServingNode:
                     body = json.dumps(body).encode()
                 self.send_response(code)
                 # server.message_compress (reference: RpcView compress, snappy/lz4/zlib): row payloads are
-                # deflated when the peer accepts it; only zlib is available in this image
-                if (ctype == "application/octet-stream" and len(body) >= 4096
-                        and "deflate" in self.headers.get("Accept-Encoding", "")):
-                    body = zlib.compress(body, 1)
-                    self.send_header("Content-Encoding", "deflate")
+                # compressed with the first codec the peer accepts (utils/compress.py: native lz4, zlib)
+                if ctype == "application/octet-stream" and len(body) >= 4096:
+                    accept = self.headers.get("Accept-Encoding", "")
+                    for enc in ("lz4", "deflate"):
+                        if enc in accept:
+                            body = _compress.compress(body, enc)
+                            self.send_header("Content-Encoding", enc)
+                            break
                 self.send_header("Content-Type", ctype)
                 self.send_header("Content-Length", str(len(body)))
                 self.end_headers()
@@ -83,8 +87,9 @@ class ServingNode:
             def _body(self):
                 n = int(self.headers.get("Content-Length", 0))
                 data = self.rfile.read(n) if n else b""
-                if self.headers.get("Content-Encoding", "") == "deflate":
-                    data = zlib.decompress(data)
+                enc = self.headers.get("Content-Encoding", "")
+                if enc in ("deflate", "lz4"):
+                    data = _compress.decompress(data, enc)
                 return data
 
             def do_GET(self):

@@ -97,6 +97,9 @@ def test_serving_message_compress():
     out_plain = ServingClient(master.endpoint).find_model_variable(sign, 0).pull(ids)
     out_z = ServingClient(master.endpoint, message_compress="zlib").find_model_variable(sign, 0).pull(ids)
     assert torch.allclose(out_plain, ref) and torch.equal(out_plain, out_z)
+    for codec in ("lz4", "snappy"):        # native LZ4 block codec (utils/compress.py) in both directions
+        out_l = ServingClient(master.endpoint, message_compress=codec).find_model_variable(sign, 0).pull(ids)
+        assert torch.equal(out_plain, out_l), codec
     node.exit()
     reset_context()
 
