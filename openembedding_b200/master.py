@@ -11,7 +11,11 @@ needs no server process and no data-plane RPC. The control plane keeps the same 
 of a ``torch.distributed.TCPStore`` (the store server thread plays the master): tree paths
 are store keys, children are tracked in an append-only per-parent index, ephemeral nodes are
 heartbeat leases (a node whose lease is older than ``LEASE_S`` is dead -- the reference drops
-them on socket close, Master.cpp:203).
+them on socket close, Master.cpp:203). Watchers (Master.cpp:247-304 notifies the registered
+connections of a node and of its parent): every mutation bumps a version counter of the node
+and of its parent and creates the notification key of that version; a watcher blocks in the
+store's server-side ``wait`` on the NEXT version's key (its own connection), so a change wakes
+it without polling.
 """
 import datetime
 import socket
@@ -91,6 +95,35 @@ class MasterClient:
         parent, _, name = p.rpartition("/")
         self._store.append(self._ik(parent), name + "\n")
 
+    # ---- change notification
+    def _wk(self, path):
+        return "w:" + self.root + self._norm(path)
+
+    def _notify(self, path):
+        """bump the version of `path` and of its parent and publish the notification keys of the new versions"""
+        p = self._norm(path)
+        targets = [p]
+        if p:
+            targets.append(p.rpartition("/")[0])
+        for t in targets:
+            ver = int(self._store.add("w:" + self.root + t, 1))
+            self._store.set("n:" + self.root + t + "#%d" % ver, "1")
+            if ver > 2:
+                try:
+                    self._store.delete_key("n:" + self.root + t + "#%d" % (ver - 2))
+                except Exception:
+                    pass
+
+    def node_version(self, path):
+        """number of changes of `path` or of one of its children so far"""
+        return int(self._store.add(self._wk(path), 0))
+
+    def watch(self, path, callback, poll_s=0.5):
+        """call ``callback(path, version)`` (on a watcher thread) after every change of `path` or of one of its direct
+        children -- add, set, delete, or an ephemeral child created / removed. Returns a handle with ``cancel()``.
+        The thread blocks server-side on the notification key of the next version (its own store connection)."""
+        return _Watch(self, path, callback, poll_s)
+
     # ---- tree
     def tree_node_add(self, path, value="", ephemeral=False):
         """create; False if the node already exists"""
@@ -104,6 +137,7 @@ class MasterClient:
             self._index_child(path)
             if ephemeral:
                 self._lease(path)
+            self._notify(path)
         return ok
 
     def tree_node_set(self, path, value):
@@ -111,6 +145,7 @@ class MasterClient:
         self._store.set(self._vk(path), value if value else " ")
         if not existed:
             self._index_child(path)
+        self._notify(path)
         return True
 
     def tree_node_get(self, path, default=None):
@@ -124,6 +159,7 @@ class MasterClient:
             return False
         self._store.set(self._vk(path), _TOMB)
         self._leases.pop(self._norm(path), None)
+        self._notify(path)
         return True
 
     def tree_node_sub(self, path):
@@ -190,6 +226,45 @@ class MasterClient:
 
     def release_lock(self, name):
         self._store.set("k:" + self.root + "/" + name, "free")
+
+
+class _Watch:
+    """one watcher: a thread with its own store connection, blocked in ``wait`` on the next version's key"""
+
+    def __init__(self, client, path, callback, poll_s):
+        from torch.distributed import TCPStore
+        ip, port = client.endpoint.rsplit(":", 1)
+        self._store = TCPStore(ip, int(port), is_master=False, timeout=datetime.timedelta(seconds=3600))
+        self._prefix = "n:" + client.root + client._norm(path) + "#"
+        self._wk = client._wk(path)
+        self.path, self.callback, self.poll_s = path, callback, poll_s
+        self.version = int(self._store.add(self._wk, 0))
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._store.wait([self._prefix + "%d" % (self.version + 1)], datetime.timedelta(seconds=self.poll_s))
+            except Exception:
+                # timeout: nothing yet (or several versions went by at once and the key was collected): resync below
+                pass
+            if self._stop.is_set():
+                return
+            try:
+                cur = int(self._store.add(self._wk, 0))
+            except Exception:
+                return
+            if cur != self.version:
+                self.version = cur
+                try:
+                    self.callback(self.path, cur)
+                except Exception:
+                    pass
+
+    def cancel(self):
+        self._stop.set()
 
 
 class Server:

@@ -59,13 +59,17 @@ class ServingClient:
         self.policy = policy
         self._dead = {}          # node_id -> time marked dead
         self._models = {}
+        self._stale, self._watches = set(), {}       # model signs whose placement record changed (master watcher)
 
     def _model(self, sign, refresh=False):
-        if refresh or sign not in self._models:
+        if refresh or sign not in self._models or sign in self._stale:
             v = self.master.tree_node_get("models/" + sign)
             if not v:
                 raise KeyError("no such model: " + sign)
+            self._stale.discard(sign)
             self._models[sign] = json.loads(v)
+            if sign not in self._watches:     # placement changes (restore after a node loss, delete) invalidate the cache
+                self._watches[sign] = self.master.watch("models/" + sign, lambda p, ver, s=sign: self._stale.add(s))
         return self._models[sign]
 
     def _nodes(self):

@@ -222,3 +222,47 @@ def test_native_model_in_process(cpu_context):
         got = m.pull(0, probe)
         assert got.shape == (2, 3, 6) and torch.allclose(got, want)
         m.close()
+
+
+def test_master_watchers():
+    """MasterClient.watch: a change of a node or of one of its children wakes the watcher (server-side wait on the
+    next version's notification key, no polling loop); reference: pico-core rpc/Master.cpp watchers"""
+    import threading
+    import time
+    import openembedding_b200 as oe
+    master = oe.Master()
+    a, b = master.client(), master.client()
+    seen, ev = [], threading.Event()
+
+    def cb(path, ver):
+        seen.append((path, ver))
+        ev.set()
+
+    w = a.watch("jobs", cb, poll_s=5.0)               # long wait: a wake-up within 2 s proves it was notified
+    v0 = a.node_version("jobs")
+    t0 = time.time()
+    assert b.tree_node_add("jobs/j1", "x")
+    assert ev.wait(2.0) and time.time() - t0 < 2.0, seen
+    assert seen[-1][0] == "jobs" and seen[-1][1] > v0
+    ev.clear()
+    b.tree_node_set("jobs/j1", "y")                  # a child's value change notifies the parent's watchers too
+    assert ev.wait(2.0)
+    ev.clear()
+    b.tree_node_del("jobs/j1")
+    assert ev.wait(2.0)
+    n = len(seen)
+    w.cancel()
+    b.tree_node_add("jobs/j2", "z")
+    time.sleep(0.3)
+    assert len(seen) == n                            # cancelled watchers stay quiet
+    # a burst of changes is coalesced, never lost: the watcher ends at the current version
+    seen2 = []
+    w2 = a.watch("burst", lambda p, v: seen2.append(v), poll_s=0.2)
+    for i in range(20):
+        b.tree_node_set("burst/k%d" % i, str(i))
+    deadline = time.time() + 3.0
+    while time.time() < deadline and (not seen2 or seen2[-1] != a.node_version("burst")):
+        time.sleep(0.05)
+    assert seen2 and seen2[-1] == a.node_version("burst") == 20
+    w2.cancel()
+    a.close(); b.close()
