@@ -71,6 +71,7 @@ class MasterClient:
         self._leases = {}
         self._hb = None
         self._stop = threading.Event()
+        self._my_watches = []
 
     # ---- key helpers
     def _norm(self, path):
@@ -198,6 +199,9 @@ class MasterClient:
 
     def close(self):
         self._stop.set()
+        for w in list(self._my_watches):
+            w.cancel(join=True)
+        self._my_watches = []
 
     # ---- ids / barriers / locks
     def generate_id(self, name):
@@ -228,6 +232,19 @@ class MasterClient:
         self._store.set("k:" + self.root + "/" + name, "free")
 
 
+_watches = []
+
+
+def _cancel_watches():
+    """interpreter exit: no watcher thread may still sit inside the store client when it is torn down"""
+    for w in list(_watches):
+        w.cancel(join=True)
+
+
+import atexit  # noqa: E402
+atexit.register(_cancel_watches)
+
+
 class _Watch:
     """one watcher: a thread with its own store connection, blocked in ``wait`` on the next version's key"""
 
@@ -241,6 +258,8 @@ class _Watch:
         self.version = int(self._store.add(self._wk, 0))
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        _watches.append(self)
+        client._my_watches.append(self)
         self._t.start()
 
     def _run(self):
@@ -263,8 +282,12 @@ class _Watch:
                 except Exception:
                     pass
 
-    def cancel(self):
+    def cancel(self, join=False):
         self._stop.set()
+        if self in _watches:
+            _watches.remove(self)
+        if join and self._t.is_alive() and threading.current_thread() is not self._t:
+            self._t.join(self.poll_s + 1.0)
 
 
 class Server:
