@@ -45,8 +45,13 @@ __global__ void __launch_bounds__(CIN_WARPS * 32) exb_cin_outer_kernel(const voi
         for (int j = lane; j < m; j += 32) s_x[warp][j] = x[(size_t)r * ld_x + j];
         __syncwarp();
         __nv_bfloat16* zr = Z + (size_t)r * ldz;
+        // (h, j) of the lane's first column, then advanced by 256 columns per iteration without dividing again
+        const int dh = 256 / m, dj = 256 - dh * m;
+        int h0 = (lane * 8) / m, j0 = lane * 8 - h0 * m;
         for (int c0 = lane * 8; c0 < Kp; c0 += 32 * 8) {       // 16 bytes per lane and iteration
-            int h = c0 / m, j = c0 - h * m;
+            int h = h0, j = j0;
+            h0 += dh; j0 += dj;
+            if (j0 >= m) { j0 -= m; ++h0; }
             __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {

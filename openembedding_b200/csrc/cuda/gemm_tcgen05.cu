@@ -743,8 +743,11 @@ int pick_bn(int M, int N, int K) {
     if (forced < 0) { const char* e = getenv("EXB_GEMM_BN"); forced = e ? atoi(e) : 0; }
     if (forced == 64 || forced == 128) return forced;
     // measured (profiles/dense_path.md): 128-wide tiles cut operand traffic by a third but leave too few
-    // CTAs in flight per SM for this step's shapes (fwd1 15.0 -> 17.0 us, dX1 32.9 -> 35.6 us); default 64
-    (void)M; (void)N; (void)K;
+    // CTAs in flight per SM for the fused step's shapes (fwd1 15.0 -> 17.0 us, dX1 32.9 -> 35.6 us); default 64.
+    // Exception: tall, short-K products (the CIN input-gradient GEMM: M 36 864, N 1 728, K 128 -- two k-blocks per
+    // tile, 7 776 tiles): a tile is all set-up + epilogue (ncu: 116 us, tensor pipe 6.6 %, DRAM 8 %), so the wider
+    // tile halves the number of those
+    if (K <= 128 && N >= 512 && M >= 8192) return 128;
     return 64;
 }
 

@@ -192,18 +192,18 @@ class _Pipeline:
                          labels=torch.zeros((batch,), dtype=torch.float32, device=dev)) for _ in range(n)]
         self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(n)]
         self.copied = [torch.cuda.Event() for _ in range(n)]
-        self.consumed = [torch.cuda.Event() for _ in range(n)]
         self.done = [torch.cuda.Event() for _ in range(n)]
         self.k = 0            # batches submitted
         self.trained = 0      # batches trained
         self.h2d_bytes = batch * num_sparse * 8 + batch * num_dense * 4 + batch * 4
         self.d2h_bytes = 4
 
-    def _train(self, j, next_ids):
+    def _train(self, j, next_ids, copied_waited=False):
         """launch the step of batch j (device buffer j % NBUF)"""
         i = j % self.NBUF
         cur = torch.cuda.current_stream(self.t.device)
-        cur.wait_event(self.copied[i])
+        if not copied_waited:
+            cur.wait_event(self.copied[i])
         if j >= self.NBUF:
             self.done[i].synchronize()                        # loss_host[i] of batch j - NBUF has landed
         d = self.dev[i]
@@ -214,16 +214,15 @@ class _Pipeline:
             loss = self.t.step(d["ids"], d["dense"], d["labels"], next_ids=next_ids)
         else:
             loss = self.t.step(d["ids"], d["dense"], d["labels"])
-        self.consumed[i].record(cur)
         self.loss_host[i].copy_(loss, non_blocking=True)
-        self.done[i].record(cur)
+        self.done[i].record(cur)      # one event: the loss has landed AND buffer i may be refilled (the copy stream waits on it)
         self.trained = j + 1
 
     def submit(self, ids_h, dense_h, labels_h):
         k = self.k
         i = k % self.NBUF
         if k >= self.NBUF:
-            self.copy_stream.wait_event(self.consumed[i])     # buffer i free again (batch k - NBUF trained)
+            self.copy_stream.wait_event(self.done[i])         # buffer i free again (batch k - NBUF trained)
         with torch.cuda.stream(self.copy_stream):
             d = self.dev[i]
             d["ids"].copy_(ids_h, non_blocking=True)
@@ -236,7 +235,8 @@ class _Pipeline:
         elif k >= 1:
             cur = torch.cuda.current_stream(self.t.device)
             cur.wait_event(self.copied[i])                    # the plan kernel of batch k reads its ids
-            self._train(k - 1, self.dev[i]["ids"])
+            # batch k-1's copy was waited for by the previous submit (as "next ids") -- except for the very first one
+            self._train(k - 1, self.dev[i]["ids"], copied_waited=k >= 2)
 
     def flush(self):
         while self.trained < self.k:
