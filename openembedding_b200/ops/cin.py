@@ -80,8 +80,12 @@ class _CinLayerFn(torch.autograd.Function):
         R, H, m, N, C, Mp, Kp, Np, relu, has_bias = ctx.dims
         dev = dy.device
         st = torch.cuda.current_stream(dev).cuda_stream
-        dyb = torch.zeros((Mp, Np), dtype=torch.bfloat16, device=dev)
+        dyb = torch.empty((Mp, Np), dtype=torch.bfloat16, device=dev)
         dyb[:R, :N] = dy * (out[:R, :N] > 0) if relu else dy
+        if N < Np:
+            dyb[:, N:].zero_()
+        if R < Mp:
+            dyb[R:, :N].zero_()
         dhid = dx = dw = db = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             WTb = Wb.t().contiguous()                                   # [Kp, Np]: K-major in N for dZ = dY W

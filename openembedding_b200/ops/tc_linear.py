@@ -21,11 +21,17 @@ def _r(x, m):
 
 
 def _pad_bf16(x, rows, cols):
-    """[r, c] float -> zero-padded bf16 [rows, cols]"""
+    """[r, c] float -> zero-padded bf16 [rows, cols]: ONE cast-copy over the data, the pad strips zeroed separately
+    (a zeros() + copy pair was two full passes over every operand: ~0.1 ms of a DCN-v2 step)"""
     if x.dtype == torch.bfloat16 and x.shape == (rows, cols) and x.is_contiguous():
         return x
-    out = torch.zeros((rows, cols), dtype=torch.bfloat16, device=x.device)
-    out[: x.shape[0], : x.shape[1]] = x
+    r, c = x.shape
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    out[:r, :c] = x
+    if c < cols:
+        out[:, c:].zero_()
+    if r < rows:
+        out[r:, :c].zero_()
     return out
 
 
@@ -42,8 +48,8 @@ class _TcLinearFn(torch.autograd.Function):
         ctx.save_for_backward(xb, weight)
         ctx.shape = (M, K, N)
         ctx.has_bias = bias is not None
-        y = out[:M, :N].float()
-        return y + bias if bias is not None else y
+        # bf16 + fp32 promotes to fp32 in one kernel (no separate .float() pass)
+        return out[:M, :N] + bias if bias is not None else out[:M, :N].float()
 
     @staticmethod
     def backward(ctx, dy):
