@@ -207,6 +207,11 @@ class MasterClient:
     def generate_id(self, name):
         return int(self._store.add("id:" + self.root + "/" + name, 1)) - 1
 
+    def advance_counter(self, name, by):
+        """atomically add `by` to a cluster-wide counter; returns its value BEFORE the addition (fetch_add)"""
+        by = int(by)
+        return int(self._store.add("c:" + self.root + "/" + name, by)) - by
+
     def barrier(self, name, n, timeout=3600):
         key = "b:" + self.root + "/" + name
         arrived = int(self._store.add(key, 1))

@@ -88,12 +88,17 @@ class ServingClient:
                 raise RuntimeError("model %s is %s" % (model_sign, rec.get("model_status")))
         return ModelVariable(self, model_sign, variable_id, rec)
 
-    def _pick(self, reps):
+    def _pick(self, reps, key=0):
         live = [r for r in reps if time.time() - self._dead.get(r, 0) > 5.0]
         if not live:
             return None
         if self.policy == "random":
             return live[np.random.randint(len(live))]
+        if self.policy == "hash":
+            # replica affinity: the same (model, shard, first id) keeps hitting the same replica -- its row cache stays
+            # warm -- and adding a replica moves only 1/n of the keys (jump consistent hash, utils/hashing.py)
+            from ..utils.hashing import jump_consistent_hash, murmur3_fmix64
+            return live[jump_consistent_hash(murmur3_fmix64(int(key)), len(live))]
         return live[next(self._rr) % len(live)]
 
     def _pull_shard(self, sign, vid, shard, local_ids, dim, np_dt, timeout):
@@ -101,7 +106,7 @@ class ServingClient:
         while True:
             rec = self._model(sign)
             reps = rec["placement"][str(shard)]
-            nid = self._pick(reps)
+            nid = self._pick(reps, key=(int(local_ids[0]) if local_ids.size else 0) * 1000003 + shard)
             nodes = self._nodes()
             if nid is None or nid not in nodes:
                 if time.time() - t0 > timeout:

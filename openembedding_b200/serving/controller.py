@@ -92,7 +92,20 @@ class ModelController:
             ids = sorted(nodes)
             S = len(ids) if shard_num in (-1, 0, None) else int(shard_num)
             R = max(1, min(int(replica_num), len(ids)))
-            placement = {str(s): [ids[(s + r) % len(ids)] for r in range(R)] for s in range(S)}
+            # rotating cursor over the nodes (Model.cpp:153-186: start = ino.fetch_add(shard_num * replica_num),
+            # node = (shard * replica_num + i + start) % n): consecutive models -- and single-shard models in
+            # particular -- do not pile up on the first node. The cursor lives in the master, so every controller
+            # of the cluster advances the same one (the reference's is per process).
+            start = self.master.advance_counter("placement_cursor", S * R)
+            placement = {}
+            for s_ in range(S):
+                reps = []
+                for r in range(R):
+                    nid = ids[(s_ * R + r + start) % len(ids)]
+                    if nid in reps:                       # R does not divide the ring evenly: next free node
+                        nid = next(x for x in ids[(ids.index(nid) + 1):] + ids if x not in reps)
+                    reps.append(nid)
+                placement[str(s_)] = reps
             rec = {"model_sign": sign, "model_uri": model_uri, "model_status": "CREATING", "model_error": "",
                    "variables": meta["variables"], "shard_num": S, "replica_num": R, "placement": placement}
             self.master.tree_node_set("models/" + sign, json.dumps(rec))

@@ -2,9 +2,10 @@
 
 Reference: pico-core ``MurmurHash3`` / ``HashFunction`` and pico-ps ``Partitioner``
 (murmur + jump-consistent-hash; pico-ps/pico-ps/common/Partitioner.h). OpenEmbedding's embedding
-tables do NOT use it (they route ``id % shard_num``, EmbeddingPullOperator.cpp:74-76); the serving
-tier uses it to spread the shards of many models over the nodes without reshuffling existing
-placements when nodes are added.
+tables do NOT use it (they route ``id % shard_num``, EmbeddingPullOperator.cpp:74-76) and its serving
+placement is a rotating cursor (Model.cpp:153-186 -> ``serving/controller.py``); the functions are the
+generic-PS utilities of the inventory, used by ``ServingClient(policy="hash")`` to keep a key range on
+one replica (cache affinity) without reshuffling when replicas are added.
 """
 
 _M64 = (1 << 64) - 1

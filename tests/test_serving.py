@@ -265,3 +265,41 @@ def test_daemon_sigkill_failover_and_restore(cpu_context):
                 p.wait(timeout=10)
             except Exception:
                 p.kill()
+
+
+def test_placement_cursor_and_hash_policy(cpu_context):
+    """single-shard models rotate over the nodes (Model.cpp:153-186 rotating cursor, cluster-wide in the master);
+    ServingClient(policy="hash") keeps a key on one replica (jump consistent hash)"""
+    import openembedding_b200 as oe
+    from openembedding_b200.serving.client import ServingClient
+    from openembedding_b200.serving.controller import ModelController
+    d = tempfile.mkdtemp()
+    sign, want_e, _ = _export_model(d)
+    master = oe.Master()
+    servers = [oe.Server(master_endpoint=master.endpoint) for _ in range(3)]
+    ctl = ModelController(master.endpoint)
+    import shutil
+    firsts, signs = [], []
+    for k in range(3):                       # the same files under three signs = three single-shard models
+        dk = d + "/copy%d" % k
+        shutil.copytree(d + "/model", dk)
+        meta = json.load(open(dk + "/model_meta"))
+        meta["model_sign"] = "%s-copy%d" % (sign, k)
+        json.dump(meta, open(dk + "/model_meta", "w"), indent=4)
+        s = ctl.create_model(dk, replica_num=2, shard_num=1)
+        signs.append(s)
+        reps = ctl.show_model(s)["placement"]["0"]
+        assert len(reps) == 2 and len(set(reps)) == 2
+        firsts.append(reps[0])
+    assert len(set(firsts)) == 3, firsts      # cursor advanced by shard_num * replica_num = 2 on a ring of 3
+    # replicas on two nodes: the hash policy sends one key to one replica, different keys spread over both
+    s = signs[0]
+    cli = ServingClient(master.endpoint, policy="hash")
+    reps = cli._model(s)["placement"]["0"]
+    picks = [cli._pick(reps, key=k) for k in range(200)]
+    assert all(cli._pick(reps, key=k) == picks[k] for k in range(200))
+    assert len(set(picks)) == len(reps)
+    v = cli.find_model_variable(s, 0)
+    assert torch.allclose(v.pull(torch.arange(0, 600)), want_e)
+    for sv in servers:
+        sv.exit()
