@@ -35,6 +35,9 @@ ap.add_argument("--prefetch", action="store_true", help="pinned-host input pipel
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--warmup", type=int, default=10)
 ap.add_argument("--cpu", action="store_true")
+ap.add_argument("--profile", default="", help="directory: write a chrome trace of 10 steps after the timed run "
+                                                "(reference: --profile / TensorBoard profile_batch, criteo_deepctr.py:290-293), "
+                                                "the vtimer table and the process RSS")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -104,6 +107,25 @@ for name in models:
         t = torch.tensor([ms], dtype=torch.float64, device=dev if use_cuda else "cpu")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if a.profile:
+            from torch.profiler import ProfilerActivity, profile
+            from openembedding_b200.utils import timers
+            os.makedirs(a.profile, exist_ok=True)
+            acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if use_cuda else [])
+            timers.enabled = True
+            with profile(activities=acts) as prof:
+                for i in range(10):
+                    step(i)
+                if use_cuda:
+                    torch.cuda.synchronize()
+            timers.enabled = False
+            trace = os.path.join(a.profile, "%s_dim%d_rank%d.trace.json" % (name, dim, ctx.rank))
+            prof.export_chrome_trace(trace)
+            if ctx.rank == 0:
+                import psutil
+                print("profile: %s ; rss %.1f GB" % (trace, psutil.Process().memory_info().rss / 2 ** 30), flush=True)
+                print(prof.key_averages().table(sort_by="cuda_time_total" if use_cuda else "cpu_time_total", row_limit=15,
+                                                max_name_column_width=60), flush=True)
         if ctx.rank == 0:
             print(json.dumps({"model": name, "embedding_dim": dim, "optimizer": a.optimizer, "n_gpus": world,
                               "batch_per_gpu": a.batch_size, "engine": "fused" if fused else "eager",
