@@ -1,5 +1,8 @@
 """ctypes bindings of the two in-tree native libraries (C ABI, see ``_build.py``).
 
+Reference: the pybind11 module ``libexb`` (openembedding/entry/py_api.cc:225-...) over the C ABI of
+openembedding/entry/c_api.h; here the C ABI is called directly (ctypes releases the GIL on every call).
+
 ``core()`` -> ``libexb_core.so`` (CPU engine + checkpoint IO), ``cuda()`` ->
 ``libexb_cuda.so`` (sm_100a kernels). Loading is lazy; a missing/stale library is
 rebuilt if a compiler is present, otherwise an ImportError explains what is missing --

@@ -1,5 +1,8 @@
 """Two-shot all-reduce (sum) over peer-mapped gradient buffers -- NVLink P2P, no NCCL.
 
+Reference: the dense gradients go through Horovod / NCCL (``hvd.DistributedOptimizer(op=hvd.Sum)``,
+test/benchmark/criteo_deepctr.py:262-263; examples/criteo_deepctr_network.py:54).
+
 Kernels: ``exb_ar_*`` in ``csrc/cuda/dense_kernels.cu``. Every rank owns a cudaMalloc'd
 gradient buffer and a flag block, both exported once with CUDA IPC; a call is ONE persistent
 kernel (flag exchange, reduce-scatter by peer loads fused with the all-gather by peer stores,
