@@ -512,7 +512,11 @@ class FusedTrainer:
 
     ``step(ids, dense, labels, next_ids=...)``: with ``next_ids`` (the device ids of the batch that will be passed
     as ``ids`` to the NEXT call) the de-duplication plan of the next batch is built inside this step on a side
-    stream -- the prefetch of the reference's ``pulling`` (exb.py:645-691)."""
+    stream -- the prefetch of the reference's ``pulling`` (exb.py:645-691).
+
+    Note on the very first call with ``use_graph=True``: before the first capture the step is run eagerly twice on
+    that first batch (allocator warm-up, lazy kernel loading -- neither may happen inside a capture), so the first
+    batch is applied three times. Every later step is exactly one graph replay."""
 
     supports_prefetch = True
     want_prefetch = True         # ``make_pipeline`` runs one batch ahead: the next batch's pull overlaps this step's tail
