@@ -452,6 +452,30 @@ class FusedCTR:
             self._grad_dirty = True
         return self.loss.view(())
 
+    def warmup(self, ids, dense, labels):
+        """Launch every kernel of a training step once WITHOUT changing a parameter: forward + backward of the batch
+        with the gradients discarded, the planned pull and push+update of a zero-row batch (all phases and barriers,
+        no row; world > 1: the ride-along all-reduce sums zero gradients), the dense optimizer on a snapshot that is
+        restored afterwards. Used before a CUDA-graph capture -- lazy kernel loading and allocator growth may not
+        happen inside one. Collective when world > 1."""
+        lib, st = self.lib, self._st()
+        keep = [t.clone() for t in (self.theta, self.accum, self.accum2, self.opt_step)]
+        self.forward_backward(ids, dense, labels, update=False)
+        g = self.group
+        none_ids, none_g = ids[:0], self.G32[:0]
+        if getattr(g, "v2", False):
+            g.pull(none_ids, out=self.X32, train=True)
+        self.gtheta.zero_()
+        g.push_update(none_ids, none_g)
+        if self._ar is not None and not self._rider:
+            self._ar()
+        _ck(lib.exb_dense_opt(ctypes.byref(self._opt_args), st), "dense_opt")
+        for t, k in zip((self.theta, self.accum, self.accum2, self.opt_step), keep):
+            t.copy_(k)
+        self.gtheta.zero_()
+        self._grad_dirty = False
+        self.refresh_weights()
+
     def kernels_per_step(self):
         """launches of our own kernels in one training step"""
         L = len(self.hidden)
@@ -514,9 +538,9 @@ class FusedTrainer:
     as ``ids`` to the NEXT call) the de-duplication plan of the next batch is built inside this step on a side
     stream -- the prefetch of the reference's ``pulling`` (exb.py:645-691).
 
-    Note on the very first call with ``use_graph=True``: before the first capture the step is run eagerly twice on
-    that first batch (allocator warm-up, lazy kernel loading -- neither may happen inside a capture), so the first
-    batch is applied three times. Every later step is exactly one graph replay."""
+    Before the first capture every kernel of the step is launched eagerly twice through ``FusedCTR.warmup`` (lazy
+    kernel loading and allocator growth may not happen inside a capture); the warm-up changes no parameter, so the
+    graph-driven trajectory is the eager one from the first step on."""
 
     supports_prefetch = True
     want_prefetch = True         # ``make_pipeline`` runs one batch ahead: the next batch's pull overlaps this step's tail
@@ -590,8 +614,8 @@ class FusedTrainer:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                for _ in range(2):
-                    self.m.forward_backward(s["ids"], s["dense"], s["labels"])
+                for _ in range(2):      # every kernel of the step runs, no parameter changes (FusedCTR.warmup)
+                    self.m.warmup(s["ids"], s["dense"], s["labels"])
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             if self.world > 1:

@@ -129,3 +129,39 @@ def test_fused_dense_optimizers_match_keras(cuda_context, cfg):
     err = float((got - ref).abs().max())
     moved = float((ref - theta0).abs().max())
     assert moved > 1e-4 and err < 2e-2 * moved + 1e-6, (cfg, err, moved)
+
+
+@pytest.mark.parametrize("dense_opt", ["adagrad", "ftrl"])
+def test_graph_trajectory_equals_eager_and_warmup_is_neutral(cuda_context, dense_opt):
+    """the eager warm-up before the first graph capture (FusedCTR.warmup: every kernel of the step, zero-row push,
+    dense optimizer on a restored snapshot) changes no parameter: same dense parameters and sparse rows after it,
+    and the graph-driven loss curve is the eager one from the first step on"""
+    from openembedding_b200.context import get_context, reset_context
+    from openembedding_b200.models.fused_dense import FusedCTR, FusedTrainer
+    vocab = [1000, 50, 20000, 7, 3000] + [300] * 21
+    B = 256
+    curves = []
+    for graph in (False, True):
+        reset_context()
+        ctx = get_context()
+        m = FusedCTR(vocab, embedding_dim=16, model="deepfm", batch=B, cache_threshold=64, lr=0.05,
+                     sparse_optimizer={"category": "adagrad", "learning_rate": 0.05},
+                     dense_optimizer={"category": dense_opt, "learning_rate": 0.05})
+        batches = [_batch(vocab, B, ctx.device, seed=s) for s in range(3)]
+        if graph:
+            theta0, acc0 = m.theta.clone(), m.accum.clone()
+            def rows():          # pad columns of the activation row are never written: start from zeros
+                out = torch.zeros((B, m.group.io_stride), dtype=torch.float32, device=ctx.device)
+                return m.group.pull(batches[0][0], out=out)
+            rows0 = rows()
+            m.warmup(*batches[0])
+            torch.cuda.synchronize()
+            assert torch.equal(m.theta, theta0) and torch.equal(m.accum, acc0)
+            assert torch.equal(rows(), rows0)
+            assert int(m.opt_step.item()) == 0
+        tr = FusedTrainer(m, use_graph=graph)
+        curves.append([float(tr.step(*batches[k % 3])) for k in range(7)])
+        torch.cuda.synchronize()
+        ctx.backend.engine.check()
+    for a, b in zip(*curves):
+        assert abs(a - b) < 2e-4, curves
