@@ -150,7 +150,10 @@ class Trainer:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(3):   # warm-up outside capture (allocator, cuBLAS handles, autotune)
+            # warm-up outside capture (allocator, cuBLAS handles, autotune): PyTorch's whole-network capture recipe --
+            # these are three REAL training steps on the first batch (the fused trainer's warm-up is parameter-neutral,
+            # FusedCTR.warmup; the autograd-driven eager zoo has no zero-row path through torch's own ops)
+            for _ in range(3):
                 self._device_step(s["ids"], s["dense"], s["labels"])
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
